@@ -1,0 +1,151 @@
+"""ctypes binding of libdost_b200.so (the C ABI declared in include/dost.h).
+
+There is no CPU fallback: if the shared library is missing or a CUDA device is not visible, every
+op raises.  Build the library with ``python -m dostransformer_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdost_b200.so")
+
+F32, F64 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_PRELU = 0, 1, 2, 3
+KC, MC = 0, 1
+
+_lib: Optional[C.CDLL] = None
+
+
+class Seg(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("ld", C.c_longlong), ("idx", C.c_void_p), ("div", C.c_int),
+                ("width", C.c_int)]
+
+
+class Gemm(C.Structure):
+    _fields_ = [
+        ("dtype", C.c_int), ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("batch", C.c_int),
+        ("a_mode", C.c_int), ("a_nseg", C.c_int), ("a", Seg * 3), ("a_bstride", C.c_longlong),
+        ("b_mode", C.c_int), ("b", Seg), ("b_bstride", C.c_longlong),
+        ("bias", C.c_void_p), ("act", C.c_int), ("act_slope", C.c_double), ("prelu_slope", C.c_void_p),
+        ("out_pre", C.c_void_p), ("ld_pre", C.c_longlong),
+        ("dact_saved", C.c_void_p), ("ld_dact", C.c_longlong), ("dact_kind", C.c_int), ("dact_slope", C.c_double),
+        ("residual", C.c_void_p), ("ld_res", C.c_longlong),
+        ("out", C.c_void_p), ("ldc", C.c_longlong), ("c_bstride", C.c_longlong),
+        ("accumulate", C.c_int), ("split_k", C.c_int),
+    ]
+
+
+_SIGNATURES = {
+    "dost_abi_version": (C.c_int, []),
+    "dost_last_error": (C.c_char_p, []),
+    "dost_launch_count": (C.c_longlong, []),
+    "dost_reset_launch_count": (None, []),
+    "dost_cast_i64_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dost_csr_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_longlong]),
+    "dost_csr_build": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(Gemm)]),
+    "dost_gemm": (C.c_int, [C.POINTER(Gemm), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_ln_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "dost_ln_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_longlong, C.c_int]),
+    "dost_ln_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                              C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_colsum_workspace_bytes": (C.c_size_t, [C.c_int, C.c_longlong, C.c_longlong]),
+    "dost_colsum": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p,
+                              C.c_size_t, C.c_void_p]),
+    "dost_prelu_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_longlong]),
+    "dost_prelu_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                 C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_segment_reduce": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong,
+                                      C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dost_gather_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dost_phonon_edge_feat": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "dost_xattn_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_double, C.c_double, C.c_ulonglong, C.c_void_p]),
+    "dost_xattn_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "dost_xattn_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_double,
+                                 C.c_double, C.c_ulonglong, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_softmax_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
+                                   C.c_double, C.c_ulonglong, C.c_void_p]),
+    "dost_softmax_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
+                                   C.c_double, C.c_ulonglong, C.c_void_p]),
+    "dost_loss_fwd": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dost_loss_bwd": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def load(path: str = LIB_PATH) -> C.CDLL:
+    """dlopen the library and attach the signatures.  Does not need a GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(path):
+        raise RuntimeError(f"{path} not found: the CUDA extension is not built (python -m dostransformer_b200.build). "
+                           "dostransformer_b200 has no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dost_abi_version() != 1:
+        raise RuntimeError("libdost_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def lib() -> C.CDLL:
+    """The loaded library, for compute calls: requires a visible CUDA device."""
+    L = load()
+    if not torch.cuda.is_available():
+        raise RuntimeError("dostransformer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().dost_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libdost_b200 {what} failed (rc={rc}): {msg}")
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise TypeError(f"dostransformer_b200 supports float32/float64 tensors, got {t.dtype}")
+
+
+def p(t: Optional[torch.Tensor]):
+    """Device pointer of a tensor (honours storage offset) or NULL."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("dostransformer_b200: tensor is not on a CUDA device (no CPU fallback)")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().dost_launch_count())
+
+
+def reset_launch_count() -> None:
+    load().dost_reset_launch_count()

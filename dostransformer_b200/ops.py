@@ -1,0 +1,617 @@
+"""Host-side operators: torch.autograd.Function wrappers around the C ABI (include/dost.h).
+
+Every device computation below is a kernel of libdost_b200.so launched on torch's current stream; torch
+only provides device memory (torch.empty) and the autograd graph.  No CPU fallback, no torch math on the
+forward or backward path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+
+NUM_SMS = 148
+
+
+def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+def _ld(t: torch.Tensor) -> int:
+    """Leading dimension (elements) of a 2-D row-strided view with unit column stride."""
+    assert t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1), "need a row-major (possibly row-strided) 2-D view"
+    return t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1])
+
+
+# =====================================================================================================
+# graph structure (integer work)
+# =====================================================================================================
+@dataclass
+class CSR:
+    rowptr: torch.Tensor      # int32 [size+1]
+    perm: Optional[torch.Tensor]  # int32 [n] or None (identity)
+    key: torch.Tensor         # int32 [n]  (the index the segments were built from)
+    size: int
+
+
+def to_i32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype == torch.int32:
+        return t.contiguous()
+    assert t.dtype == torch.int64, f"index tensor must be int64/int32, got {t.dtype}"
+    t = t.contiguous()
+    out = torch.empty(t.shape, dtype=torch.int32, device=t.device)
+    L.check(L.lib().dost_cast_i64_i32(L.p(t), L.p(out), t.numel(), L.stream()), "cast_i64_i32")
+    return out
+
+
+def csr_build(key32: torch.Tensor, size: int, want_max: bool = False) -> Tuple[CSR, Optional[torch.Tensor]]:
+    n = key32.numel()
+    dev = key32.device
+    rowptr = torch.empty(size + 1, dtype=torch.int32, device=dev)
+    perm = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    mx = torch.empty(1, dtype=torch.int32, device=dev) if want_max else None
+    lib = L.lib()
+    nb = lib.dost_csr_workspace_bytes(n, size)
+    ws = _ws(nb, dev)
+    L.check(lib.dost_csr_build(L.p(key32), n, size, L.p(rowptr), L.p(perm), L.p(mx), L.p(ws), nb, L.stream()), "csr_build")
+    return CSR(rowptr, perm[:n], key32, size), mx
+
+
+@dataclass
+class CrystalGraph:
+    """Integer structure of one batch, built once and shared by all layers and the backward pass."""
+    N: int
+    E: int
+    B: int
+    row: torch.Tensor
+    col: torch.Tensor
+    batch: torch.Tensor
+    system: torch.Tensor
+    by_dst: CSR          # edges grouped by destination (col): scatter_sum / scatter_mean order
+    by_src: CSR          # edges grouped by source (row): adjoint of x[row]
+    by_system: CSR       # crystals grouped by crystal system: adjoint of promt_token[g.system]
+    crystals: CSR        # nodes grouped by crystal (contiguous): ptr = crystals.rowptr
+    nmax: torch.Tensor   # int32 [1] on device: max nodes per crystal (to_dense_batch padding length)
+    _trows: dict = field(default_factory=dict)
+
+    @property
+    def ptr(self) -> torch.Tensor:
+        return self.crystals.rowptr
+
+    def token_rowptr(self, T: int) -> torch.Tensor:
+        """rowptr of the [B*T] token rows grouped by crystal (T contiguous rows each)."""
+        if T not in self._trows:
+            self._trows[T] = torch.arange(0, (self.B + 1) * T, T, dtype=torch.int32, device=self.row.device)
+        return self._trows[T]
+
+
+def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Tensor, *, nmax_override: Optional[int] = None,
+                need_backward: bool = True) -> CrystalGraph:
+    """edge_index int64 [2,E] (row = centre atom, col = neighbour), batch int64 [N] sorted, system int64 [B]."""
+    assert edge_index.is_cuda, "dostransformer_b200 has no CPU path: move the batch to a CUDA device"
+    N, E, B = batch.numel(), edge_index.shape[1], system.numel()
+    ei = to_i32(edge_index)
+    row, col = ei[0], ei[1]
+    b32, s32 = to_i32(batch), to_i32(system)
+    by_dst, _ = csr_build(col, N)
+    by_src = by_sys = None
+    if need_backward:
+        by_src, _ = csr_build(row, N)
+        by_sys, _ = csr_build(s32, 7)
+    crystals, nmax = csr_build(b32, B, want_max=True)
+    crystals.perm = None
+    if nmax_override is not None:     # data-parallel: global padding length fixed by the sharder
+        nmax = torch.full((1,), int(nmax_override), dtype=torch.int32, device=batch.device)
+    return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax)
+
+
+# =====================================================================================================
+# raw kernel wrappers (no autograd)
+# =====================================================================================================
+@dataclass
+class RowMap:
+    """How A-operand row m of a GEMM maps to a row of ``tensor``: row = idx[m // div] (idx optional)."""
+    idx: Optional[torch.Tensor] = None
+    div: int = 1
+    # adjoint information (needed for the backward of the mapped operand)
+    csr: Optional[CSR] = None            # groups target rows by source row (for idx maps)
+    div_rowptr: Optional[torch.Tensor] = None  # contiguous groups of `div` rows
+
+
+def _seg(t: torch.Tensor, m: Optional[RowMap], width: int) -> L.Seg:
+    s = L.Seg()
+    s.base = t.data_ptr()
+    s.ld = _ld(t)
+    s.idx = m.idx.data_ptr() if (m is not None and m.idx is not None) else None
+    s.div = m.div if m is not None else 1
+    s.width = width
+    return s
+
+
+def gemm_raw(*, M: int, N: int, K: int, a: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], a_mode: int,
+             b: torch.Tensor, b_mode: int, b_map: Optional[RowMap] = None, out: torch.Tensor,
+             bias: Optional[torch.Tensor] = None, act: int = L.ACT_NONE, act_slope: float = 0.0,
+             prelu_slope: Optional[torch.Tensor] = None, out_pre: Optional[torch.Tensor] = None,
+             dact_saved: Optional[torch.Tensor] = None, dact_kind: int = L.ACT_NONE, dact_slope: float = 0.0,
+             residual: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
+             batch: int = 1, a_bstride: int = 0, b_bstride: int = 0, c_bstride: int = 0,
+             ldb: Optional[int] = None, ldc: Optional[int] = None, lda: Optional[int] = None) -> None:
+    g = L.Gemm()
+    g.dtype = L.dt(out)
+    g.M, g.N, g.K, g.batch = M, N, K, batch
+    g.a_mode, g.a_nseg = a_mode, len(a)
+    for i, (t, m) in enumerate(a):
+        width = t.shape[-1] if a_mode == L.KC else K
+        g.a[i] = _seg(t if t.dim() == 2 else t.reshape(-1, t.shape[-1]), m, width)
+        if lda is not None:
+            g.a[i].ld = lda
+    g.a_bstride = a_bstride
+    g.b_mode = b_mode
+    g.b = _seg(b if b.dim() == 2 else b.reshape(-1, b.shape[-1]), b_map, 0)
+    if ldb is not None:
+        g.b.ld = ldb
+    g.b_bstride = b_bstride
+    g.bias = bias.data_ptr() if bias is not None else None
+    g.act, g.act_slope = act, act_slope
+    g.prelu_slope = prelu_slope.data_ptr() if prelu_slope is not None else None
+    if out_pre is not None:
+        g.out_pre, g.ld_pre = out_pre.data_ptr(), _ld(out_pre.reshape(-1, out_pre.shape[-1]))
+    if dact_saved is not None:
+        g.dact_saved, g.ld_dact = dact_saved.data_ptr(), _ld(dact_saved.reshape(-1, dact_saved.shape[-1]))
+        g.dact_kind, g.dact_slope = dact_kind, dact_slope
+    if residual is not None:
+        g.residual, g.ld_res = residual.data_ptr(), _ld(residual.reshape(-1, residual.shape[-1]))
+    g.out = out.data_ptr()
+    g.ldc = ldc if ldc is not None else _ld(out if out.dim() == 2 else out.reshape(-1, out.shape[-1]))
+    g.c_bstride = c_bstride
+    g.accumulate = 1 if accumulate else 0
+    g.split_k = split_k
+    lib = L.lib()
+    ws, nb = None, 0
+    if split_k > 1:
+        nb = lib.dost_gemm_workspace_bytes(C.byref(g))
+        ws = _ws(nb, out.device)
+    L.check(lib.dost_gemm(C.byref(g), L.p(ws), nb, L.stream()), "gemm")
+
+
+def _pick_split(M_out: int, N_out: int, K_red: int, elem: int) -> int:
+    tile = 128 if elem == 4 else 64
+    tiles = math.ceil(M_out / tile) * math.ceil(N_out / tile)
+    want = max(1, (4 * NUM_SMS) // tiles)
+    return int(max(1, min(want, math.ceil(K_red / 256), 512)))
+
+
+def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, W = x2d.shape
+    if out is None:
+        out = torch.empty(W, dtype=x2d.dtype, device=x2d.device)
+    lib = L.lib()
+    nb = lib.dost_colsum_workspace_bytes(L.dt(x2d), M, W)
+    ws = _ws(nb, x2d.device)
+    L.check(lib.dost_colsum(L.dt(x2d), L.p(x2d), _ld(x2d), M, W, L.p(out), L.p(ws), nb, L.stream()), "colsum")
+    return out
+
+
+def segment_reduce_raw(src: torch.Tensor, rowptr: torch.Tensor, perm: Optional[torch.Tensor], nseg: int, *,
+                       mean: bool = False, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    W = src.shape[1]
+    if out is None:
+        assert not accumulate
+        out = torch.empty(nseg, W, dtype=src.dtype, device=src.device)
+    L.check(L.lib().dost_segment_reduce(L.dt(src), L.p(src), _ld(src), L.p(rowptr), L.p(perm), nseg, W,
+                                        1 if mean else 0, 1 if accumulate else 0, L.p(out), _ld(out), L.stream()),
+            "segment_reduce")
+    return out
+
+
+def gather_rows_raw(src: torch.Tensor, idx: torch.Tensor, *, deg_rowptr: Optional[torch.Tensor] = None,
+                    add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    R, W = idx.numel(), src.shape[1]
+    out = torch.empty(R, W, dtype=src.dtype, device=src.device)
+    L.check(L.lib().dost_gather_rows(L.dt(src), L.p(src), _ld(src), L.p(idx), L.p(deg_rowptr), L.p(add),
+                                     _ld(add) if add is not None else 0, R, W, L.p(out), _ld(out), L.stream()),
+            "gather_rows")
+    return out
+
+
+# =====================================================================================================
+# Linear with gather/concat prologue and fused epilogue
+# =====================================================================================================
+@dataclass
+class LinearSpec:
+    maps: List[Optional[RowMap]]     # one per A segment
+    tensor_of_seg: List[int]         # which input tensor each segment reads (lets x feed two segments)
+    M: int
+    act: int = L.ACT_NONE
+    act_slope: float = 0.0
+    want_pre: bool = False           # also return the pre-activation / pre-residual value
+
+
+class _Linear(torch.autograd.Function):
+    """y = act(cat_s(X_s[map_s]) @ W^T + b) (+ residual); optionally also returns the pre-activation value.
+
+    args: spec, weight [N,K], bias [N]|None, prelu_slope [1]|None, residual [M,N]|None, *tensors
+    """
+
+    @staticmethod
+    def forward(ctx, spec: LinearSpec, weight, bias, slope, residual, *tensors):
+        N, K = weight.shape
+        M = spec.M
+        dev = weight.device
+        segs = [(tensors[ti], spec.maps[si]) for si, ti in enumerate(spec.tensor_of_seg)]
+        out = torch.empty(M, N, dtype=weight.dtype, device=dev)
+        need_pre = spec.want_pre or spec.act == L.ACT_PRELU
+        pre = torch.empty(M, N, dtype=weight.dtype, device=dev) if need_pre else None
+        gemm_raw(M=M, N=N, K=K, a=segs, a_mode=L.KC, b=weight, b_mode=L.KC, out=out, bias=bias, act=spec.act,
+                 act_slope=spec.act_slope, prelu_slope=slope, out_pre=pre, residual=residual)
+        ctx.spec = spec
+        ctx.n_tensors = len(tensors)
+        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        saved_act = None
+        if spec.act in (L.ACT_RELU, L.ACT_LEAKY):
+            saved_act = out
+        elif spec.act == L.ACT_PRELU:
+            saved_act = pre
+        ctx.save_for_backward(weight, slope, saved_act, *tensors)
+        if spec.want_pre:
+            return out, pre
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out, d_pre=None):
+        spec: LinearSpec = ctx.spec
+        weight, slope, saved_act, *tensors = ctx.saved_tensors
+        N, K = weight.shape
+        M = spec.M
+        dev, dtype = weight.device, weight.dtype
+        d_out = d_out.contiguous()
+        d_res = d_out if ctx.has_res else None
+        d_slope = None
+        # ---- gradient wrt the pre-activation value v
+        if spec.act == L.ACT_PRELU:
+            dv = torch.empty_like(d_out)
+            d_slope = torch.empty(1, dtype=dtype, device=dev)
+            lib = L.lib()
+            nb = lib.dost_prelu_bwd_workspace_bytes(L.dt(d_out), d_out.numel())
+            ws = _ws(nb, dev)
+            L.check(lib.dost_prelu_bwd(L.dt(d_out), L.p(d_out), L.p(saved_act), L.p(slope), L.p(dv), L.p(d_slope),
+                                       d_out.numel(), L.p(ws), nb, L.stream()), "prelu_bwd")
+            dact = None
+        elif spec.act in (L.ACT_RELU, L.ACT_LEAKY):
+            # dv = d_out * act'(out): the PReLU-backward kernel with a constant slope (sign(out) == sign(v) here)
+            dv = torch.empty_like(d_out)
+            cslope = _const(spec.act_slope if spec.act == L.ACT_LEAKY else 0.0, dtype, dev)
+            junk = torch.empty(1, dtype=dtype, device=dev)
+            lib = L.lib()
+            nb = lib.dost_prelu_bwd_workspace_bytes(L.dt(d_out), d_out.numel())
+            ws = _ws(nb, dev)
+            L.check(lib.dost_prelu_bwd(L.dt(d_out), L.p(d_out), L.p(saved_act), L.p(cslope), L.p(dv), L.p(junk),
+                                       d_out.numel(), L.p(ws), nb, L.stream()), "act_bwd")
+            dact = None
+        else:
+            dv = d_out
+            if spec.want_pre and d_pre is not None:
+                # v feeds both outputs: out = v + residual and pre = v
+                dv = torch.empty_like(d_out)
+                _axpy2(d_out, d_pre.contiguous(), dv)
+        needs = ctx.needs_input_grad
+        # ---- bias
+        d_bias = colsum(dv) if (ctx.has_bias and needs[2]) else None
+        # ---- weight: dW[:, kseg] = dv^T @ X_s[map]   (reduction over the M rows, deterministic split-K)
+        d_weight = None
+        if needs[1]:
+            d_weight = torch.empty(N, K, dtype=dtype, device=dev)
+            k0 = 0
+            for si, ti in enumerate(spec.tensor_of_seg):
+                t = tensors[ti]
+                w = t.shape[-1]
+                split = _pick_split(N, w, M, weight.element_size())
+                gemm_raw(M=N, N=w, K=M, a=[(dv, None)], a_mode=L.MC, b=t, b_mode=L.MC, b_map=spec.maps[si],
+                         out=d_weight[:, k0:k0 + w], ldc=K, split_k=split)
+                k0 += w
+        # ---- inputs: dA = dv @ W  [M, K], then the adjoint of each row map
+        d_tensors: List[Optional[torch.Tensor]] = [None] * ctx.n_tensors
+        tens_needs = needs[5:]
+        if any(tens_needs):
+            dA = torch.empty(M, K, dtype=dtype, device=dev)
+            gemm_raw(M=M, N=K, K=N, a=[(dv, None)], a_mode=L.KC, b=weight, b_mode=L.MC, out=dA)
+            k0 = 0
+            for si, ti in enumerate(spec.tensor_of_seg):
+                t = tensors[ti]
+                w = t.shape[-1]
+                if tens_needs[ti]:
+                    piece = dA[:, k0:k0 + w]
+                    d_tensors[ti] = _map_adjoint(piece, spec.maps[si], t.shape[0], d_tensors[ti])
+                k0 += w
+        return (None, d_weight, d_bias, d_slope, d_res, *d_tensors)
+
+
+def _axpy2(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
+    """out = a + b through the row-gather kernel (identity rows), keeping elementwise math in our kernels."""
+    R, W = a.shape
+    idx = _arange_i32(R, a.device)
+    L.check(L.lib().dost_gather_rows(L.dt(a), L.p(a), _ld(a), L.p(idx), None, L.p(b), _ld(b), R, W, L.p(out), _ld(out),
+                                     L.stream()), "add")
+
+
+_ARANGE_CACHE = {}
+_CONST_CACHE = {}
+
+
+def _const(value: float, dtype, device) -> torch.Tensor:
+    key = (float(value), dtype, str(device))
+    if key not in _CONST_CACHE:
+        _CONST_CACHE[key] = torch.full((1,), float(value), dtype=dtype, device=device)
+    return _CONST_CACHE[key]
+
+
+def _arange_i32(n: int, device) -> torch.Tensor:
+    key = (str(device), )
+    cur = _ARANGE_CACHE.get(key)
+    if cur is None or cur.numel() < n:
+        cur = torch.arange(max(n, 1 << 16), dtype=torch.int32, device=device)
+        _ARANGE_CACHE[key] = cur
+    return cur[:n]
+
+
+def _map_adjoint(piece: torch.Tensor, m: Optional[RowMap], n_src_rows: int, acc: Optional[torch.Tensor]) -> torch.Tensor:
+    """Adjoint of row gather/broadcast: reduce the [M, w] gradient onto the source rows (fixed order)."""
+    if m is None or (m.idx is None and m.div == 1):
+        if acc is None:
+            return piece
+        out = torch.empty_like(acc)
+        _axpy2(acc, piece, out)
+        return out
+    cur = piece
+    if m.div > 1:
+        assert m.div_rowptr is not None
+        groups = m.div_rowptr.numel() - 1
+        if m.idx is None:
+            return segment_reduce_raw(cur, m.div_rowptr, None, groups, out=acc, accumulate=acc is not None)
+        cur = segment_reduce_raw(cur, m.div_rowptr, None, groups)
+    assert m.csr is not None, "row map used in a differentiable position needs its CSR"
+    if acc is None:
+        return segment_reduce_raw(cur, m.csr.rowptr, m.csr.perm, n_src_rows)
+    return segment_reduce_raw(cur, m.csr.rowptr, m.csr.perm, n_src_rows, out=acc, accumulate=True)
+
+
+def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: torch.Tensor,
+           bias: Optional[torch.Tensor], *, M: Optional[int] = None, act: int = L.ACT_NONE, act_slope: float = 0.0,
+           prelu_slope: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+           want_pre: bool = False):
+    """Fused Linear.  ``segments`` are concatenated along the feature axis; a tensor may appear in several."""
+    tensors: List[torch.Tensor] = []
+    tos: List[int] = []
+    for t, _ in segments:
+        for i, u in enumerate(tensors):
+            if u is t:
+                tos.append(i)
+                break
+        else:
+            tensors.append(t)
+            tos.append(len(tensors) - 1)
+    if M is None:
+        t0, m0 = segments[0]
+        assert m0 is None or (m0.idx is None and m0.div == 1)
+        M = t0.shape[0]
+    spec = LinearSpec([m for _, m in segments], tos, M, act, act_slope, want_pre)
+    return _Linear.apply(spec, weight, bias, prelu_slope, residual, *tensors)
+
+
+# =====================================================================================================
+# LayerNorm (+PReLU)
+# =====================================================================================================
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, slope):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M, W = x2.shape
+        y = torch.empty(M, W, dtype=x.dtype, device=x.device)
+        stats = torch.empty(M, 2, dtype=x.dtype, device=x.device)
+        L.check(L.lib().dost_ln_fwd(L.dt(x), L.p(x2), _ld(x2), L.p(gamma), L.p(beta), L.p(slope), L.p(y), L.p(stats), M, W,
+                                    L.stream()), "ln_fwd")
+        ctx.save_for_backward(x2, gamma, beta, slope, stats)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gamma, beta, slope, stats = ctx.saved_tensors
+        M, W = x2.shape
+        dy2 = dy.reshape(M, W)
+        if dy2.stride(-1) != 1:
+            dy2 = dy2.contiguous()
+        dev, dtype = x2.device, x2.dtype
+        dx = torch.empty(M, W, dtype=dtype, device=dev)
+        dg = torch.empty(W, dtype=dtype, device=dev)
+        db = torch.empty(W, dtype=dtype, device=dev)
+        ds = torch.empty(1, dtype=dtype, device=dev) if slope is not None else None
+        lib = L.lib()
+        nb = lib.dost_ln_bwd_workspace_bytes(L.dt(x2), M, W)
+        ws = _ws(nb, dev)
+        L.check(lib.dost_ln_bwd(L.dt(x2), L.p(dy2), _ld(dy2), L.p(x2), _ld(x2), L.p(stats), L.p(gamma), L.p(beta),
+                                L.p(slope), L.p(dx), L.p(dg), L.p(db), L.p(ds), M, W, L.p(ws), nb, L.stream()), "ln_bwd")
+        return dx.view(ctx.shape), dg, db, ds
+
+
+def layer_norm(x, gamma, beta, prelu_slope=None):
+    return _LayerNorm.apply(x, gamma, beta, prelu_slope)
+
+
+# =====================================================================================================
+# segmented reduction (scatter_sum / scatter_mean / pooling)
+# =====================================================================================================
+class _SegmentReduce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, csr: CSR, mean: bool):
+        ctx.csr, ctx.mean = csr, mean
+        return segment_reduce_raw(src.contiguous(), csr.rowptr, csr.perm, csr.size, mean=mean)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        csr: CSR = ctx.csr
+        d_src = gather_rows_raw(d_out.contiguous(), csr.key, deg_rowptr=csr.rowptr if ctx.mean else None)
+        return d_src, None, None
+
+
+def segment_reduce(src, csr: CSR, mean: bool = False):
+    return _SegmentReduce.apply(src, csr, mean)
+
+
+# =====================================================================================================
+# cross attention energy tokens -> atoms (ragged, phantom keys)
+# =====================================================================================================
+class _CrossAttention(torch.autograd.Function):
+    """out = resid + softmax(q kv^T / sqrt(H)) kv over the atoms of each sequence's crystal plus
+    (nmax - n_b) phantom keys equal to ``phantom``.  q/resid: [S,T,H] or [T,H] (broadcast over S)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float, seed: int):
+        H = kv.shape[1]
+        T = q.shape[-2]
+        q, resid = q.contiguous(), resid.contiguous()
+        q_ss = T * H if q.dim() == 3 else 0
+        r_ss = T * H if resid.dim() == 3 else 0
+        out = torch.empty(S, T, H, dtype=kv.dtype, device=kv.device)
+        lse = torch.empty(S, T, dtype=torch.float32, device=kv.device)
+        scale = float(H) ** -0.5
+        L.check(L.lib().dost_xattn_fwd(L.dt(kv), L.p(q), q_ss, L.p(kv), L.p(phantom), L.p(graph.ptr), L.p(graph.nmax),
+                                       L.p(resid), r_ss, L.p(out), L.p(lse), S, graph.B, T, H, scale, drop_p, seed,
+                                       L.stream()), "xattn_fwd")
+        ctx.save_for_backward(q, kv, phantom, resid, out, lse)
+        ctx.graph, ctx.S, ctx.drop_p, ctx.seed = graph, S, drop_p, seed
+        ctx.q_ss, ctx.r_ss = q_ss, r_ss
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, kv, phantom, resid, out, lse = ctx.saved_tensors
+        g: CrystalGraph = ctx.graph
+        S = ctx.S
+        H, T = kv.shape[1], out.shape[1]
+        d_out = d_out.contiguous()
+        dev, dtype = kv.device, kv.dtype
+        dq = torch.empty(S, T, H, dtype=dtype, device=dev)
+        dkv = torch.empty_like(kv)
+        dph = torch.empty(H, dtype=dtype, device=dev)
+        lib = L.lib()
+        nb = lib.dost_xattn_bwd_workspace_bytes(L.dt(kv), S, T, H)
+        ws = _ws(nb, dev)
+        L.check(lib.dost_xattn_bwd(L.dt(kv), L.p(d_out), L.p(q), ctx.q_ss, L.p(kv), L.p(phantom), L.p(g.ptr), L.p(g.batch),
+                                   L.p(g.nmax), L.p(out), L.p(resid), ctx.r_ss, L.p(lse), L.p(dq), L.p(dkv), L.p(dph),
+                                   S, g.B, T, H, g.N, float(H) ** -0.5, ctx.drop_p, ctx.seed, L.p(ws), nb, L.stream()),
+                "xattn_bwd")
+        d_q = dq if ctx.q_ss else colsum(dq.view(S, T * H)).view(T, H)
+        d_resid = d_out if ctx.r_ss else colsum(d_out.view(S, T * H)).view(T, H)
+        return d_q, dkv, dph, d_resid, None, None, None, None
+
+
+def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float = 0.0, seed: int = 0):
+    return _CrossAttention.apply(q, kv, phantom, resid, graph, S, drop_p, seed)
+
+
+# =====================================================================================================
+# dense self attention over the T energy tokens of each sequence
+# =====================================================================================================
+class _SelfAttention(torch.autograd.Function):
+    """out = resid + softmax_fp32(q k^T / sqrt(H)) k, per sequence; q, resid: [S,Lq,H], k (= v): [S,Lk,H]."""
+
+    @staticmethod
+    def forward(ctx, q, k, resid, drop_p: float, seed: int):
+        S, Lq, H = q.shape
+        Lk = k.shape[1]
+        q, k, resid = q.contiguous(), k.contiguous(), resid.contiguous()
+        dev, dtype = q.device, q.dtype
+        Lp = (Lk + 3) // 4 * 4          # padded row length of the score matrices: keeps 16-byte vector loads legal
+        scores = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
+        gemm_raw(M=Lq, N=Lk, K=H, a=[(q.view(S * Lq, H), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.KC,
+                 out=scores, batch=S, a_bstride=Lq * H, b_bstride=Lk * H, c_bstride=Lq * Lp, ldc=Lp)
+        pd = torch.empty_like(scores) if drop_p > 0 else scores
+        L.check(L.lib().dost_softmax_fwd(L.dt(q), L.p(scores), L.p(scores), L.p(pd), S * Lq, Lk, Lp, float(H) ** -0.5,
+                                         drop_p, seed, L.stream()), "softmax_fwd")
+        out = torch.empty(S, Lq, H, dtype=dtype, device=dev)
+        gemm_raw(M=Lq, N=H, K=Lk, a=[(pd.view(S * Lq, Lp), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.MC,
+                 out=out, residual=resid, batch=S, a_bstride=Lq * Lp, b_bstride=Lk * H, c_bstride=Lq * H, ldc=H, lda=Lp)
+        ctx.save_for_backward(q, k, scores, pd if drop_p > 0 else None)
+        ctx.drop_p, ctx.seed = drop_p, seed
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        q, k, prob, pd = ctx.saved_tensors
+        if pd is None:
+            pd = prob
+        S, Lq, H = q.shape
+        Lk, Lp = k.shape[1], prob.shape[2]
+        d_out = d_out.contiguous()
+        dev, dtype = q.device, q.dtype
+        scale = float(H) ** -0.5
+        # dPd = dO k^T
+        dpd = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
+        gemm_raw(M=Lq, N=Lk, K=H, a=[(d_out.view(S * Lq, H), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.KC,
+                 out=dpd, batch=S, a_bstride=Lq * H, b_bstride=Lk * H, c_bstride=Lq * Lp, ldc=Lp)
+        ds = dpd  # in place
+        L.check(L.lib().dost_softmax_bwd(L.dt(q), L.p(prob), L.p(dpd), L.p(ds), S * Lq, Lk, Lp, scale, ctx.drop_p,
+                                         ctx.seed, L.stream()), "softmax_bwd")
+        # dQ = dS k
+        dq = torch.empty(S, Lq, H, dtype=dtype, device=dev)
+        gemm_raw(M=Lq, N=H, K=Lk, a=[(ds.view(S * Lq, Lp), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.MC,
+                 out=dq, batch=S, a_bstride=Lq * Lp, b_bstride=Lk * H, c_bstride=Lq * H, ldc=H, lda=Lp)
+        # dK = dS^T q + Pd^T dO   (reduction over the Lq queries)
+        dk = torch.empty(S, Lk, H, dtype=dtype, device=dev)
+        gemm_raw(M=Lk, N=H, K=Lq, a=[(ds.view(S * Lq, Lp), None)], a_mode=L.MC, b=q.view(S * Lq, H), b_mode=L.MC,
+                 out=dk, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp)
+        gemm_raw(M=Lk, N=H, K=Lq, a=[(pd.view(S * Lq, Lp), None)], a_mode=L.MC, b=d_out.view(S * Lq, H), b_mode=L.MC,
+                 out=dk, accumulate=True, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp)
+        return dq, dk, d_out, None, None
+
+
+def self_attention(q, k, resid, drop_p: float = 0.0, seed: int = 0):
+    return _SelfAttention.apply(q, k, resid, drop_p, seed)
+
+
+# =====================================================================================================
+# loss
+# =====================================================================================================
+class _DosLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred_g, pred_s, target, mode: int, beta: float):
+        B, T = pred_g.shape
+        pred_g, pred_s = pred_g.contiguous(), pred_s.contiguous()
+        target = target.reshape(B, T).contiguous()
+        loss = torch.empty(1, dtype=pred_g.dtype, device=pred_g.device)
+        saved = torch.empty(4 * B, dtype=pred_g.dtype, device=pred_g.device)
+        L.check(L.lib().dost_loss_fwd(L.dt(pred_g), mode, L.p(pred_g), L.p(pred_s), L.p(target), beta, B, T, L.p(loss),
+                                      L.p(saved), L.stream()), "loss_fwd")
+        ctx.save_for_backward(pred_g, pred_s, target, saved)
+        ctx.mode, ctx.beta = mode, beta
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        pred_g, pred_s, target, saved = ctx.saved_tensors
+        B, T = pred_g.shape
+        g = g.contiguous()
+        dg, ds = torch.empty_like(pred_g), torch.empty_like(pred_s)
+        L.check(L.lib().dost_loss_bwd(L.dt(pred_g), ctx.mode, L.p(pred_g), L.p(pred_s), L.p(target), ctx.beta, B, T,
+                                      L.p(saved), L.p(g), L.p(dg), L.p(ds), L.stream()), "loss_bwd")
+        return dg, ds, None, None, None
+
+
+def dos_loss(pred_global, pred_system, target, *, mode: str = "edos", beta: float = 1.0):
+    """mode 'edos': main_eDOS.py:111-123 (targets clamped at 0, per-crystal RMSE); 'phonon': main_phDOS.py:109-114."""
+    return _DosLoss.apply(pred_global, pred_system, target, 0 if mode == "edos" else 1, float(beta))
+
+
+def phonon_edge_features(edge_vec: torch.Tensor) -> torch.Tensor:
+    ev = edge_vec.contiguous()
+    out = torch.empty(ev.shape[0], 4, dtype=ev.dtype, device=ev.device)
+    L.check(L.lib().dost_phonon_edge_feat(L.dt(ev), L.p(ev), ev.shape[0], L.p(out), L.stream()), "phonon_edge_feat")
+    return out

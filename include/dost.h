@@ -1,0 +1,188 @@
+/*
+ * dost.h -- C ABI of libdost_b200.so: the sm_100a kernels behind the DOSTransformer hot path.
+ *
+ * The reference (HeewoongNoh/DOSTransformer) is pure Python: it has no FFI of its own.  Every device
+ * op on its hot path is a library call into ATen/cuBLAS or one of three un-vendored packages
+ * (SURVEY.md section 2.2, rows k1-k22).  This header is therefore the native surface the replacement
+ * *creates*: each entry point names the reference call site(s) (file:line under /root/reference) it
+ * takes over.  The host side (python, dostransformer_b200/) binds these with ctypes; INTEGRATION.md
+ * shows the stub.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no torch / pybind types.
+ *   - every device buffer (inputs, outputs, workspace) is caller-owned; the library never allocates,
+ *     frees or synchronises.  Work is ordered only by the `stream` argument (a cudaStream_t).
+ *   - return value: 0 = ok, negative = DOST_ERR_*; dost_last_error() gives a thread-local message.
+ *   - dtype: DOST_F32 (eDOS, reference default) or DOST_F64 (phonon: main_phDOS.py:15-16 sets float64).
+ *   - index arrays are int32 (dost_cast_i64_i32 converts the int64 PyG tensors once per batch).
+ *   - stateless and re-entrant; one host thread per GPU in data-parallel runs.
+ */
+#ifndef DOST_H_
+#define DOST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOST_ABI_VERSION 1
+
+enum { DOST_F32 = 0, DOST_F64 = 1 };
+enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
+enum { DOST_ACT_NONE = 0, DOST_ACT_RELU = 1, DOST_ACT_LEAKY = 2, DOST_ACT_PRELU = 3 };
+enum { DOST_KC = 0 /* reduction index contiguous */, DOST_MC = 1 /* row/col index contiguous */ };
+
+typedef void* dost_stream_t; /* cudaStream_t */
+
+int dost_abi_version(void);
+const char* dost_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long dost_launch_count(void);
+void dost_reset_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Integer graph structure (bit-exact work).  Replaces the index handling implied by
+ * torch_scatter.scatter_sum/mean (DOSTransformer.py:187, DOSTransformer_phonon.py:209),
+ * to_dense_batch (DOSTransformer.py:61) and len(batch.unique()) (DOSTransformer.py:118).
+ * ------------------------------------------------------------------------------------------- */
+int dost_cast_i64_i32(const int64_t* src, int32_t* dst, long long n, dost_stream_t stream);
+
+/* Stable counting sort of element ids 0..n-1 by key[i] in [0,size):  rowptr[size+1], perm[n] with
+ * perm == argsort(key, stable).  maxcount (optional, 1 int) receives max segment length.
+ * workspace: dost_csr_workspace_bytes(n, size). */
+size_t dost_csr_workspace_bytes(long long n, long long size);
+int dost_csr_build(const int32_t* key, long long n, long long size, int32_t* rowptr, int32_t* perm,
+                   int32_t* maxcount, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * GEMM family (fp32/fp64 FMA path).  C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ).
+ * Replaces nn.Linear / torch.bmm / torch.cat / x[row] / .repeat on the path:
+ * DOSTransformer.py:103-105,116-120 (encoders), :139-143,174-175 (gather+cat+edge_mlp), :188-190
+ * (node_mlp_2), :65-69,79-83 (repeat+cat+fc/fc_prompt), :75,89 (out_layer), :158-159 (decoder);
+ * layers/transformer.py:143-145 (fc1/fc2); layers/multihead_attention.py:68,72 (bmm) and the
+ * autograd backward of each (main_eDOS.py:126).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* base;   /* device pointer */
+  long long ld;       /* leading dimension in elements */
+  const int32_t* idx; /* optional row map: row(r) = idx[r / div]; NULL: row(r) = r / div */
+  int div;            /* >= 1; T for per-crystal broadcast rows */
+  int width;          /* columns this segment contributes to the reduction dim (KC, A side) */
+} dost_seg_t;
+
+typedef struct {
+  int dtype;
+  int M, N, K;
+  int batch;                 /* >= 1: independent problems, strides below (no row maps when > 1) */
+  /* A operand: mode KC: A(m,k) = seg_s.base[row_s(m) * ld_s + (k - kstart_s)], up to 3 segments
+   * concatenated along k (segment widths must be multiples of 16 when nseg > 1).
+   * mode MC: A(m,k) = seg0.base[k * ld + m] (single segment, no map). */
+  int a_mode, a_nseg;
+  dost_seg_t a[3];
+  long long a_bstride;
+  /* B operand: KC: B(n,k) = base[n*ld + k];  MC: B(n,k) = base[row(k)*ld + n] (row map on k allowed). */
+  int b_mode;
+  dost_seg_t b;
+  long long b_bstride;
+  /* epilogue: v = acc + bias[n]; out_pre = v; v = act(v); v *= dact(saved); v += residual; out (+)= v */
+  const void* bias;
+  int act;
+  double act_slope;          /* LEAKY slope */
+  const void* prelu_slope;   /* PRELU: device pointer to the single learnable slope */
+  void* out_pre; long long ld_pre;
+  const void* dact_saved; long long ld_dact; int dact_kind; double dact_slope; /* multiply by act'(saved) */
+  const void* residual; long long ld_res;
+  void* out; long long ldc; long long c_bstride;
+  int accumulate;            /* out += v instead of out = v */
+  int split_k;               /* >= 1; > 1 needs workspace of split_k*M*N elements, reduced in fixed order */
+} dost_gemm_t;
+
+size_t dost_gemm_workspace_bytes(const dost_gemm_t* g);
+int dost_gemm(const dost_gemm_t* g, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row kernels: LayerNorm (eps = 1e-5, affine) optionally followed by PReLU -- nn.LayerNorm + nn.PReLU
+ * in edge_mlp / node_mlp_2 (DOSTransformer.py:171,182) and layers/transformer.py:132-134,142,168-170.
+ * stats[M,2] = (mean, rstd).  Backward writes dx and per-block partial sums (workspace) that
+ * dost_colsum-style fixed-order reduction turns into dgamma/dbeta/dslope (deterministic).
+ * ------------------------------------------------------------------------------------------- */
+int dost_ln_fwd(int dtype, const void* x, long long ldx, const void* gamma, const void* beta, const void* prelu_slope,
+                void* y, void* stats, long long M, int W, dost_stream_t stream);
+size_t dost_ln_bwd_workspace_bytes(int dtype, long long M, int W);
+int dost_ln_bwd(int dtype, const void* dy, long long ld_dy, const void* x, long long ldx, const void* stats,
+                const void* gamma, const void* beta, const void* prelu_slope, void* dx, void* dgamma, void* dbeta,
+                void* dslope, long long M, int W, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* out[w] = sum_m x[m*ld + w] in a fixed order (bias gradients, broadcast-row gradients). */
+size_t dost_colsum_workspace_bytes(int dtype, long long M, long long W);
+int dost_colsum(int dtype, const void* x, long long ld, long long M, long long W, void* out, void* workspace,
+                size_t workspace_bytes, dost_stream_t stream);
+
+/* PReLU backward for Linear->PReLU->Linear encoders (DOSTransformer.py:103-105): dz = da * (z>0 ? 1 : a),
+ * dslope = sum da * z * [z<=0] (fixed order). */
+size_t dost_prelu_bwd_workspace_bytes(int dtype, long long n);
+int dost_prelu_bwd(int dtype, const void* da, const void* z, const void* slope, void* dz, void* dslope, long long n,
+                   void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Segmented reductions and gathers: scatter_sum / scatter_mean (DOSTransformer.py:158,187;
+ * DOSTransformer_phonon.py:180,209; utils.py:91) as CSR reductions, and the adjoint of x[row], x[col]
+ * (DOSTransformer.py:143).  out[s, :W] (+)= scale_s * sum_{j in [rowptr[s], rowptr[s+1])} src[perm[j]*ld + :W]
+ * with scale_s = 1 (sum) or 1/max(count,1) (mean); perm == NULL means identity (contiguous segments).
+ * ------------------------------------------------------------------------------------------- */
+int dost_segment_reduce(int dtype, const void* src, long long ld, const int32_t* rowptr, const int32_t* perm,
+                        long long nseg, int W, int mean, int accumulate, void* out, long long ldo,
+                        dost_stream_t stream);
+/* out[r, :W] = src[idx[r]*ld + :W] * (deg_rowptr ? 1/max(deg(idx[r]),1) : 1) + (add ? add[r*ld_add + :W] : 0) */
+int dost_gather_rows(int dtype, const void* src, long long ld, const int32_t* idx, const int32_t* deg_rowptr,
+                     const void* add, long long ld_add, long long R, int W, void* out, long long ldo,
+                     dost_stream_t stream);
+
+/* Phonon edge features: smooth_cutoff(|v|/4) * [1, sqrt(3) v/|v|] (DOSTransformer_phonon.py:75-77). */
+int dost_phonon_edge_feat(int dtype, const void* edge_vec, long long E, void* out, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Ragged energy->atom cross attention with analytic phantom keys: to_dense_batch zero padding +
+ * LayerNorm + projection-free single-head attention (DOSTransformer.py:61-63,73,87;
+ * layers/transformer.py:132-138; layers/multihead_attention.py:68-72).  q [S,T,H] (already LN'd;
+ * q_sstride = 0 broadcasts one [T,H] block), kv [N,H] (already LN'd), phantom [H] = that layer's
+ * layer_norms[0].bias (what LN maps a zero-padded row to), ptr [B+1] crystal offsets, sequence s
+ * attends to crystal s % B and sees (*nmax - n_b) phantom keys.  out = resid + softmax(q k^T scale) k.
+ * lse [S,T] float.  Dropout (training, p>0) acts on probabilities with a counter-based mask.
+ * ------------------------------------------------------------------------------------------- */
+int dost_xattn_fwd(int dtype, const void* q, long long q_sstride, const void* kv, const void* phantom,
+                   const int32_t* ptr, const int32_t* nmax, const void* resid, long long resid_sstride, void* out,
+                   float* lse, int S, int B, int T, int H, double scale, double drop_p, unsigned long long seed,
+                   dost_stream_t stream);
+size_t dost_xattn_bwd_workspace_bytes(int dtype, int S, int T, int H);
+/* dq [S,T,H], dkv [N,H] (overwritten), dphantom [H]; attn_out = out - resid is recomputed from o_attn. */
+int dost_xattn_bwd(int dtype, const void* d_out, const void* q, long long q_sstride, const void* kv,
+                   const void* phantom, const int32_t* ptr, const int32_t* node_crystal, const int32_t* nmax,
+                   const void* out, const void* resid, long long resid_sstride, const float* lse, void* dq,
+                   void* dkv, void* dphantom, int S, int B, int T, int H, long long N, double scale, double drop_p,
+                   unsigned long long seed, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* Row softmax for the dense T x T self attention (layers/multihead_attention.py:68-70): p = softmax_fp32(s*scale);
+ * pd = dropout(p); rows are ld elements apart (ld >= cols).  Backward: ds = scale * p * (dp - sum(dp*p)) with dp = mask/(1-p) * dpd. */
+int dost_softmax_fwd(int dtype, const void* s, void* p, void* pd, long long rows, int cols, long long ld, double scale,
+                     double drop_p, unsigned long long seed, dost_stream_t stream);
+int dost_softmax_bwd(int dtype, const void* p, const void* dpd, void* ds, long long rows, int cols, long long ld, double scale,
+                     double drop_p, unsigned long long seed, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * DOS loss.  mode 0 (eDOS, main_eDOS.py:111-123): y = max(y,0); per-crystal RMSE; mean over crystals;
+ * loss = rmse_global + beta * rmse_system.  mode 1 (phonon, main_phDOS.py:109-114): sqrt of batch-wide MSE.
+ * saved [4*B]: [0,2B) per-crystal rmse (mode 0) / [0,2) batch rmse (mode 1) for the backward; [2B,4B) scratch.
+ * ------------------------------------------------------------------------------------------- */
+int dost_loss_fwd(int dtype, int mode, const void* pred_g, const void* pred_s, const void* y, double beta, int B,
+                  int T, void* loss, void* saved, dost_stream_t stream);
+int dost_loss_bwd(int dtype, int mode, const void* pred_g, const void* pred_s, const void* y, double beta, int B,
+                  int T, const void* saved, const void* grad_loss, void* d_pred_g, void* d_pred_s,
+                  dost_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOST_H_ */

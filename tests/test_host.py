@@ -1,0 +1,127 @@
+"""CPU tests of the host-side logic: init parity with the reference, state_dict layout, synthetic batches,
+the C-ABI library (loads, exports every declared symbol) and the loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from dostransformer_b200 import _lib
+from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+from dostransformer_b200.embedder_phDOS.DOSTransformer_phonon import DOSTransformer_phonon
+from dostransformer_b200.synthetic import make_edos_batch, make_large_cell_batch, make_phonon_batch
+
+
+def _summ_ok(model, fx):
+    sd = model.state_dict()
+    assert [(k, tuple(v.shape), str(v.dtype)) for k, v in sd.items()] == fx["state_keys"]
+    for k, s in fx["weights"].items():
+        v = sd[k]
+        assert abs(v.double().norm().item() - s["norm"]) <= 1e-12 * max(1.0, s["norm"]), k
+        assert torch.equal(v.flatten()[:8], s["head"]), k
+
+
+def test_edos_init_and_state_dict_match_reference():
+    fx = load_golden("edos_h256.pt")
+    torch.manual_seed(fx["init_seed"])
+    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device("cpu"), 0.0)
+    _summ_ok(m, fx)
+    assert sum(p.numel() for p in m.parameters()) == 9_428_109
+
+
+def test_phonon_init_and_state_dict_match_reference():
+    fx = load_golden("phonon_h256.pt")
+    torch.set_default_dtype(torch.float64)
+    torch.manual_seed(fx["init_seed"])
+    m = DOSTransformer_phonon(3, 2, 118, 4, 256, torch.device("cpu"), 0.0)
+    _summ_ok(m, fx)
+    assert m.fc.weight.dtype == torch.float64
+
+
+def test_phonon_ctor_accepts_the_launchers_argument_order():
+    # main_phDOS.py:68 passes (layers, transformer, 118, 4, hidden, out_dim, device)
+    m = DOSTransformer_phonon(1, 1, 118, 4, 32, 51, torch.device("cpu"))
+    assert m.n_energies == 51 and m.attn_drop == 0.0 and m.embeddings.weight.shape == (51, 32)
+    m2 = DOSTransformer_phonon(1, 1, 118, 4, 32, torch.device("cpu"), 0.1)
+    assert m2.attn_drop == 0.1
+
+
+def test_small_fixture_state_dict_loads():
+    fx = load_golden("edos_small.pt")
+    m = DOSTransformer(*fx["ctor_args"])
+    m.load_state_dict(fx["state_dict"], strict=True)
+
+
+def test_no_cpu_fallback():
+    m = DOSTransformer(1, 1, 200, 41, 2, 32, "cpu", 0.0)
+    g = make_edos_batch(2, seed=1, mean_atoms=4.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(g)
+
+
+def test_dropin_aliases():
+    import dostransformer_b200
+    dostransformer_b200.install_dropin()
+    from embedder_eDOS.DOSTransformer import DOSTransformer as A
+    from embedder_phDOS.DOSTransformer_phonon import DOSTransformer_phonon as Bc
+    from layers import TransformerEncoder
+    assert A is DOSTransformer and Bc is DOSTransformer_phonon and TransformerEncoder is not None
+    import sys
+    for k in ("embedder_eDOS", "embedder_phDOS", "layers", "embedder_eDOS.DOSTransformer",
+              "embedder_phDOS.DOSTransformer_phonon"):
+        sys.modules.pop(k, None)
+
+
+def test_synthetic_edos_layout():
+    g = make_edos_batch(16, seed=3)
+    B = 16
+    n = torch.bincount(g.batch, minlength=B)
+    assert g.x.shape[1] == 200 and g.edge_attr.shape[1] == 41 and g.glob.shape == (2 * B,)
+    assert g.y_ft.shape == (B * 201,) and len(g.mp_id) == B and g.system.max() < 7
+    assert torch.all(g.batch[1:] >= g.batch[:-1])
+    last = n.cumsum(0) - 1
+    assert torch.all(g.x[last] == 0)                      # the zero "prompt" node of every crystal
+    row, col = g.edge_index
+    assert g.edge_index.shape[1] == 12 * int((n - 1).sum())
+    assert torch.all(g.batch[row] == g.batch[col])
+    assert not torch.isin(row, last).any() and not torch.isin(col, last).any()
+    assert (g.y_ft < 0).any() and g.y_ft.max() <= 1.0 + 1e-6
+    g2 = make_edos_batch(16, seed=3)
+    assert torch.equal(g.x, g2.x) and torch.equal(g.edge_index, g2.edge_index)
+
+
+def test_synthetic_phonon_and_large_cell():
+    g = make_phonon_batch(3, seed=4)
+    assert g.x.dtype == torch.float64 and g.x.shape[1] == 118 and g.phdos.shape == (3, 51)
+    row, col = g.edge_index
+    assert g.edge_vec.shape == (row.numel(), 3)
+    self_edges = row == col
+    assert torch.all(g.edge_vec[::24] == 0) and self_edges[::24].all()
+    assert "edge_index" in g and g["edge_vec"] is g.edge_vec
+    big = make_large_cell_batch(2, seed=5)
+    n = torch.bincount(big.batch)
+    assert n.min() >= 201 and big.edge_index.shape[1] == 24 * int((n - 1).sum())
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "dost.h")).read()
+    declared = set(re.findall(r"\b(dost_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/dost.h but not exported"
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert lib.dost_abi_version() == 1
+    # argument validation works without a GPU (no launch happens)
+    assert lib.dost_gemm(None, None, 0, None) == -1
+    assert b"null descriptor" in lib.dost_last_error()
+    assert isinstance(lib.dost_csr_workspace_bytes(10, 4), int)
+
+
+def test_ops_raise_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()
