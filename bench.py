@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- train-step crystals/sec (fwd+bwd) of the eDOS DOSTransformer on synthetic crystal graphs.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl product|reference] [--batch B_PER_GPU]
+
+Workload (BASELINE.json configs[1]/[2]): DOSTransformer(3 GNN, 2 transformer layers, hidden 256), eDOS random-split
+shape (~20 atoms/crystal log-normal, 12 neighbours, 200-d node features, 41-d edge features,
+T = 201), B crystals per GPU (default 512), data-parallel over crystals with weak scaling (per-GPU batch fixed).
+A step = graph prep + forward + loss + backward (+ gradient all-reduce when N > 1); no optimizer, no data loading,
+as the metric is defined.
+
+One JSON line is printed by rank 0.  `value` is measured with the batches resident in HBM; `e2e` repeats the same
+steps from pinned host batches (H2D inside the timed region, loss read back every step).  `--impl reference` times
+the CPU oracle port of the reference (the reference itself is pure Python and cannot travel to the GPU box;
+oracle/dost_oracle.py restates it and is pinned against it by tests/golden) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train-step crystals/sec (fwd+bwd)"
+UNIT = "crystals/s"
+HIDDEN, GNN_LAYERS, T_LAYERS, T = 256, 3, 2, 201
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d["bf16_tflops"]), tensor_sustained=float(
+            d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batches(rank: int, nb: int, B: int):
+    from dostransformer_b200.synthetic import make_edos_batch
+    return [make_edos_batch(B, seed=2000 + 1000 * rank + i) for i in range(nb)]
+
+
+def flops_per_crystal_fwd(n_nodes: float, n_edges: float, nmax: float) -> float:
+    """SURVEY.md 8d formula (forward FLOPs per crystal), H=256, L=3, t=2."""
+    H, L, t = HIDDEN, GNN_LAYERS, T_LAYERS
+    Fa, Fe, Fg = 200, 41, 2
+    f = 2 * n_nodes * (Fa * H + H * H) + 2 * n_edges * (Fe * H + H * H) + 2 * (Fg * H + H * H)
+    f += L * 2 * n_edges * (3 * H * 2 * H + 2 * H * H) + L * 2 * n_nodes * (2 * H * 2 * H + 2 * H * H)
+    f += 3 * t * 4 * T * nmax * H + 2 * t * 4 * T * T * H + 5 * t * 2 * T * (8 * H * H)
+    f += 2 * T * (2 * H * H) + 2 * T * (2.5 * H * H) + 4 * T * H + 2 * (2 * H * H)
+    return f
+
+
+def cpu_port_throughput(sample_B: int, steps: int, warmup: int, threads: int, seed: int = 2000):
+    """fwd+bwd of the CPU oracle port on `sample_B` crystals of the same generator; returns (crystals/s, ms/step)."""
+    from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+    from dostransformer_b200.synthetic import make_edos_batch
+    from oracle import dost_oracle as O
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    sd = O.state_dict_of(DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, "cpu", 0.0))
+    g = make_edos_batch(sample_B, seed=seed)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.run_train_step(O.edos_forward, O.edos_loss, sd, g, g.y_ft)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return sample_B / med, med * 1e3, sum(times)
+
+
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample
+    val, ms, _ = cpu_port_throughput(sample, args.steps, args.warmup, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, random-split shape; "
+                               f"bounded sample of {sample} crystals per step (CPU)", "sample_crystals": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} crystals/step, median of {args.steps} steps, oracle/dost_oracle.py "
+                                   "(torch CPU restatement of the reference, pinned by tests/golden)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_kernel(fn, iters=10):
+    fn()
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(iters):
+        fn()
+    b.record(st)
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters * 1e-3
+
+
+def kernel_rooflines(B: int, pk):
+    """Times the dominant kernels alone, on the stream they are launched on, at the shapes the step uses."""
+    from dostransformer_b200 import _lib as L
+    from dostransformer_b200 import ops
+    dev = torch.device("cuda")
+    out = {}
+    # FFN fc1: [B*T, 256] x [1024, 256]^T  (the FFN is ~65% of the model's FLOPs)
+    M, N, K = B * T, 4 * HIDDEN, HIDDEN
+    a = torch.randn(M, K, device=dev)
+    w = torch.randn(N, K, device=dev)
+    bias = torch.randn(N, device=dev)
+    o = torch.empty(M, N, device=dev)
+    sec = time_kernel(lambda: ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=o, bias=bias,
+                                           act=L.ACT_RELU))
+    tf = 2.0 * M * N * K / sec / 1e12
+    out["roofline"] = {"kernel": "gemm_kernel<float,KC,KC> (FFN fc1 shape, fp32 FMA pipe)", "bound": "tensor",
+                       "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
+                       "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
+                       "algorithmic_flops_per_launch": 2.0 * M * N * K, "launch_ms": sec * 1e3,
+                       "fp32_fma_peak_tflops": 2 * 128 * 148 * 1.965e9 / 1e12}
+    del a, w, o
+    # scatter_sum as a CSR segmented reduction: [E,256] -> [N,256]
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(B, seed=2000)
+    gr = ops.build_graph(g.edge_index.to(dev), g.batch.to(dev), g.system.to(dev))
+    src = torch.randn(gr.E, HIDDEN, device=dev)
+    dst = torch.empty(gr.N, HIDDEN, device=dev)
+    big = [torch.randn(gr.E, HIDDEN, device=dev) for _ in range(max(1, int(300e6 // (gr.E * HIDDEN * 4))))]
+    it = {"i": 0}
+
+    def seg():
+        s = big[it["i"] % len(big)]
+        it["i"] += 1
+        ops.segment_reduce_raw(s, gr.by_dst.rowptr, gr.by_dst.perm, gr.N, out=dst)
+
+    sec = time_kernel(seg, iters=max(10, len(big) * 3))
+    nbytes = 4.0 * HIDDEN * (gr.E + gr.N) + 4.0 * gr.E + 4.0 * (gr.N + 1)
+    gbs = nbytes / sec / 1e9
+    out["roofline_hbm"] = {"kernel": "segment_reduce_vec_kernel<float,2> (scatter_sum [E,256]->[N,256])", "bound": "hbm",
+                           "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                           "algorithmic_bytes_per_launch": nbytes, "launch_ms": sec * 1e3, "E": gr.E, "N": gr.N,
+                           "note": "inputs rotated over >300 MB so they do not sit in L2"}
+    return out
+
+
+def run_product(args, rank: int, world: int, local_rank: int):
+    import torch.distributed as dist
+    from dostransformer_b200 import _lib as L
+    from dostransformer_b200 import ops
+    from dostransformer_b200.dp import GradReducer, live_named_parameters
+    from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; dostransformer_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.lib()
+    pk = peaks()
+    B = args.batch
+    NB = 3
+    host = [b.pin_memory() for b in make_batches(rank, NB, B)]
+    nmax = max(int(torch.bincount(b.batch).max()) for b in host)
+    n_nodes = sum(b.batch.numel() for b in host) / NB
+    n_edges = sum(b.edge_index.shape[1] for b in host) / NB
+    if world > 1:
+        t = torch.tensor([nmax], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        nmax = int(t.item())
+    torch.manual_seed(0)
+    model = DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, dev, 0.0).to(dev).train()
+    model.max_num_nodes = nmax            # global padding length: the only cross-rank coupling besides the grads
+    reducer = GradReducer(live_named_parameters(model)) if world > 1 else None
+    weight = 1.0 / world
+    resident = [b.clone().to(dev) for b in host]
+
+    def step(g):
+        model.zero_grad(set_to_none=True)
+        dg, _, ds = model(g)
+        loss = ops.dos_loss(dg, ds, g.y_ft, mode="edos", beta=1.0)
+        if world > 1:
+            loss = loss * weight
+        loss.backward()
+        if reducer is not None:
+            reducer.finish()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident timing
+    for i in range(args.warmup):
+        step(resident[i % NB])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    st = torch.cuda.current_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = L.launch_count()
+    e0.record(st)
+    for i in range(args.steps):
+        step(resident[i % NB])
+    e1.record(st)
+    barrier()
+    launches = L.launch_count() - l0
+    sec = e0.elapsed_time(e1) * 1e-3
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sec = float(t.item())
+    value = world * B * args.steps / sec
+
+    # ---------------------------------------------------------------- end-to-end timing (host batches)
+    h2d = host[0].nbytes()
+    for i in range(min(2, args.warmup)):
+        step(_to_device(host[i % NB], dev)).item()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        loss = step(_to_device(host[i % NB], dev))      # H2D of the whole batch from pinned memory
+        loss.item()                                     # D2H of the step's result
+    barrier()
+    e2e_sec = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e_val = world * B * args.steps / e2e_sec
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, random-split shape "
+                               f"(BASELINE configs[1]/[2]), {B} crystals per GPU", "crystals_per_gpu": B,
+                   "global_batch": B * world, "parallelism": f"dp{world}", "mean_nodes_per_batch": n_nodes,
+                   "mean_edges_per_batch": n_edges, "nmax": nmax, "precision": "fp32 FMA (fp32 parity path)",
+                   "l2_policy": "3 distinct batches rotated; per-step activations (>1 GB) exceed the 126 MB L2"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_sec / args.steps * 1e3,
+                "api": "DOSTransformer(batch) + ops.dos_loss + loss.backward(), batch copied from pinned host memory"},
+    }
+    fl = 3.0 * B * flops_per_crystal_fwd(n_nodes / B, n_edges / B, nmax)
+    line["model_tflops"] = fl * args.steps / sec / 1e12
+    if world == 1:
+        try:
+            line.update(kernel_rooflines(B, pk))
+        except Exception as ex:  # keep the headline even if the side measurement fails
+            line["roofline"] = {"error": repr(ex)}
+        if not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            val, ms, total = cpu_port_throughput(args.cpu_sample, 2, 1, threads)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"{args.cpu_sample} crystals/step of the same generator, median of 2 steps "
+                                              f"after 1 warm-up ({total:.1f} s of CPU work), oracle/dost_oracle.py"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _to_device(g, dev):
+    from dostransformer_b200.synthetic import CrystalBatch
+    return CrystalBatch(**{k: (getattr(g, k).to(dev, non_blocking=True) if torch.is_tensor(getattr(g, k)) else
+                               getattr(g, k)) for k in g.keys()})
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="product", choices=["product", "reference"])
+    ap.add_argument("--batch", type=int, default=512, help="crystals per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=16, help="crystals per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_product(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,405 @@
+"""GPU parity tests of the individual kernels (through the C ABI via dostransformer_b200.ops) against plain
+torch restatements.  Integer work is bit-exact; floating point tolerances are written at each assert."""
+import math
+
+import pytest
+import torch
+
+from conftest import relerr
+from dostransformer_b200 import _lib as L
+from dostransformer_b200 import ops
+from dostransformer_b200.ops import RowMap
+from oracle import dost_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float32: 2e-5, torch.float64: 1e-12}
+
+
+def _rand(*shape, dtype=torch.float32, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g, dtype=torch.float64) * scale).to(dtype).to(DEV)
+
+
+# --------------------------------------------------------------------------------------------- integer structure
+@pytest.mark.parametrize("n,size,hub", [(1000, 37, False), (5000, 300, True), (12, 7, False), (1, 5, False),
+                                        (100000, 9000, True)])
+def test_csr_build_bit_exact(n, size, hub):
+    g = torch.Generator().manual_seed(n)
+    key = torch.randint(0, size, (n,), generator=g)
+    if hub:
+        key[torch.rand(n, generator=g) < 0.3] = size // 2       # a hub destination (index-0 padding in mat2graph.py)
+        key[key == 3] = 4                                        # and an empty segment
+    rowptr_ref, perm_ref = O.csr_by_key(key, size)
+    csr, mx = ops.csr_build(ops.to_i32(key.to(DEV)), size, want_max=True)
+    assert torch.equal(csr.rowptr.cpu().long(), rowptr_ref)
+    assert torch.equal(csr.perm.cpu().long(), perm_ref)
+    assert int(mx.item()) == int(torch.bincount(key, minlength=size).max())
+
+
+def test_build_graph_matches_oracle():
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(9, seed=11)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV))
+    ptr, nmax = O.crystal_ptr(g.batch)
+    assert torch.equal(gr.ptr.cpu().long(), ptr) and int(gr.nmax.item()) == nmax
+    rp, pm = O.csr_by_key(g.edge_index[1], g.batch.numel())
+    assert torch.equal(gr.by_dst.rowptr.cpu().long(), rp) and torch.equal(gr.by_dst.perm.cpu().long(), pm)
+    rp, pm = O.csr_by_key(g.edge_index[0], g.batch.numel())
+    assert torch.equal(gr.by_src.rowptr.cpu().long(), rp) and torch.equal(gr.by_src.perm.cpu().long(), pm)
+    rp, pm = O.csr_by_key(g.system, 7)
+    assert torch.equal(gr.by_system.rowptr.cpu().long(), rp) and torch.equal(gr.by_system.perm.cpu().long(), pm)
+
+
+# --------------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("M,N,K", [(300, 70, 41), (129, 257, 200), (5, 1, 64), (1024, 512, 768), (64, 64, 2)])
+def test_gemm_plain_and_epilogues(dtype, M, N, K):
+    a, w, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2), _rand(N, dtype=dtype, seed=3)
+    res = _rand(M, N, dtype=dtype, seed=4)
+    out = torch.empty(M, N, dtype=dtype, device=DEV)
+    pre = torch.empty(M, N, dtype=dtype, device=DEV)
+    slope = torch.tensor([0.25], dtype=dtype, device=DEV)
+    ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=out, bias=b, act=L.ACT_PRELU,
+                 prelu_slope=slope, out_pre=pre, residual=res)
+    v = a.double() @ w.double().T + b.double()
+    ref = torch.nn.functional.prelu(v, slope.double()) + res.double()
+    assert relerr(pre, v) < TOL[dtype] * 5
+    assert relerr(out, ref) < TOL[dtype] * 5
+    ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=out, act=L.ACT_RELU)
+    assert relerr(out, torch.relu(a.double() @ w.double().T)) < TOL[dtype] * 5
+    ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=out, act=L.ACT_LEAKY, act_slope=0.01,
+                 accumulate=True)
+    ref2 = torch.relu(a.double() @ w.double().T) + torch.nn.functional.leaky_relu(a.double() @ w.double().T, 0.01)
+    assert relerr(out, ref2) < TOL[dtype] * 5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_gemm_modes_and_splitk(dtype):
+    M, N, K = 777, 96, 130
+    dy, x, w = _rand(M, N, dtype=dtype, seed=1), _rand(M, K, dtype=dtype, seed=2), _rand(N, K, dtype=dtype, seed=3)
+    # dX = dY @ W  (B read N-contiguous)
+    dx = torch.empty(M, K, dtype=dtype, device=DEV)
+    ops.gemm_raw(M=M, N=K, K=N, a=[(dy, None)], a_mode=L.KC, b=w, b_mode=L.MC, out=dx)
+    assert relerr(dx, dy.double() @ w.double()) < TOL[dtype] * 5
+    # dW = dY^T @ X with deterministic split-K, written into a column slice of a wider matrix
+    dw_full = torch.zeros(N, K + 32, dtype=dtype, device=DEV)
+    for split in (1, 5):
+        ops.gemm_raw(M=N, N=K, K=M, a=[(dy, None)], a_mode=L.MC, b=x, b_mode=L.MC, out=dw_full[:, 32:], ldc=K + 32,
+                     split_k=split)
+        assert relerr(dw_full[:, 32:], dy.double().T @ x.double()) < TOL[dtype] * 10
+        assert dw_full[:, :32].abs().max() == 0
+    # gathered reduction rows: dW = dY^T @ X[idx]
+    idx = torch.randint(0, 50, (M,), dtype=torch.int32, device=DEV)
+    xs = _rand(50, K, dtype=dtype, seed=5)
+    dw = torch.empty(N, K, dtype=dtype, device=DEV)
+    ops.gemm_raw(M=N, N=K, K=M, a=[(dy, None)], a_mode=L.MC, b=xs, b_mode=L.MC, b_map=RowMap(idx=idx), out=dw, split_k=3)
+    assert relerr(dw, dy.double().T @ xs.double()[idx.long()]) < TOL[dtype] * 10
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_gemm_gather_concat_and_batched(dtype):
+    E, Nn, H = 500, 60, 32
+    x, e = _rand(Nn, H, dtype=dtype, seed=1), _rand(E, H, dtype=dtype, seed=2)
+    w = _rand(2 * H, 3 * H, dtype=dtype, seed=3)
+    row = torch.randint(0, Nn, (E,), dtype=torch.int32, device=DEV)
+    col = torch.randint(0, Nn, (E,), dtype=torch.int32, device=DEV)
+    out = torch.empty(E, 2 * H, dtype=dtype, device=DEV)
+    ops.gemm_raw(M=E, N=2 * H, K=3 * H, a=[(x, RowMap(idx=row)), (x, RowMap(idx=col)), (e, None)], a_mode=L.KC, b=w,
+                 b_mode=L.KC, out=out)
+    cat = torch.cat([x[row.long()], x[col.long()], e], 1).double()
+    assert relerr(out, cat @ w.double().T) < TOL[dtype] * 5
+    # per-crystal broadcast rows and an index + broadcast map (fc_prompt shape)
+    B, T = 7, 11
+    en, gv, tab = _rand(B * T, H, dtype=dtype, seed=4), _rand(B, H, dtype=dtype, seed=5), _rand(7, 16, dtype=dtype, seed=6)
+    sysid = torch.randint(0, 7, (B,), dtype=torch.int32, device=DEV)
+    w2 = _rand(H, 2 * H + 16, dtype=dtype, seed=7)
+    out2 = torch.empty(B * T, H, dtype=dtype, device=DEV)
+    ops.gemm_raw(M=B * T, N=H, K=2 * H + 16, a=[(en, None), (gv, RowMap(div=T)), (tab, RowMap(idx=sysid, div=T))],
+                 a_mode=L.KC, b=w2, b_mode=L.KC, out=out2)
+    cat2 = torch.cat([en, gv.repeat_interleave(T, 0), tab[sysid.long()].repeat_interleave(T, 0)], 1).double()
+    assert relerr(out2, cat2 @ w2.double().T) < TOL[dtype] * 5
+    # batched NT with padded ldc
+    S, T2 = 5, 13
+    q, k = _rand(S, T2, H, dtype=dtype, seed=8), _rand(S, T2, H, dtype=dtype, seed=9)
+    sc = torch.zeros(S, T2, 16, dtype=dtype, device=DEV)
+    ops.gemm_raw(M=T2, N=T2, K=H, a=[(q.view(-1, H), None)], a_mode=L.KC, b=k.view(-1, H), b_mode=L.KC, out=sc, batch=S,
+                 a_bstride=T2 * H, b_bstride=T2 * H, c_bstride=T2 * 16, ldc=16)
+    assert relerr(sc[:, :, :T2], torch.bmm(q.double(), k.double().transpose(1, 2))) < TOL[dtype] * 5
+    assert sc[:, :, T2:].abs().max() == 0
+
+
+# --------------------------------------------------------------------------------------------- autograd ops
+def _grads(fn, inputs):
+    for t in inputs:
+        t.grad = None
+    out = fn()
+    outs = out if isinstance(out, (tuple, list)) else [out]
+    g = torch.Generator().manual_seed(99)
+    total = 0
+    for o in outs:
+        wgt = torch.randn(o.shape, generator=g, dtype=torch.float64).to(o.dtype).to(o.device)
+        total = total + (o * wgt).sum()
+    total.backward()
+    return [o.detach() for o in outs], [t.grad.detach().clone() if t.grad is not None else None for t in inputs]
+
+
+def _leaf(t):
+    return t.detach().clone().requires_grad_(True)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_linear_autograd_edge_mlp_shape(dtype):
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(5, seed=21, mean_atoms=6.0)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV))
+    H = 32
+    x, e = _leaf(_rand(gr.N, H, dtype=dtype, seed=1)), _leaf(_rand(gr.E, H, dtype=dtype, seed=2))
+    w, b = _leaf(_rand(2 * H, 3 * H, dtype=dtype, seed=3, scale=0.2)), _leaf(_rand(2 * H, dtype=dtype, seed=4))
+    res = _leaf(_rand(gr.E, 2 * H, dtype=dtype, seed=5))
+    row, col = g.edge_index[0].to(DEV), g.edge_index[1].to(DEV)
+
+    def mine():
+        segs = [(x, RowMap(idx=gr.row, csr=gr.by_src)), (x, RowMap(idx=gr.col, csr=gr.by_dst)), (e, None)]
+        return ops.linear(segs, w, b, M=gr.E, residual=res, want_pre=True)
+
+    def ref():
+        v = torch.nn.functional.linear(torch.cat([x[row], x[col], e], 1), w, b)
+        return v + res, v
+
+    o1, g1 = _grads(mine, [x, e, w, b, res])
+    o2, g2 = _grads(ref, [x, e, w, b, res])
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < TOL[dtype] * 20
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("act", ["prelu", "relu", "leaky", "none"])
+def test_linear_autograd_activations(dtype, act):
+    M, K, N = 333, 41, 48
+    x, w, b = _leaf(_rand(M, K, dtype=dtype, seed=1)), _leaf(_rand(N, K, dtype=dtype, seed=2)), _leaf(_rand(N, dtype=dtype, seed=3))
+    slope = _leaf(torch.tensor([0.25], dtype=dtype, device=DEV))
+    kw = {"prelu": dict(act=L.ACT_PRELU, prelu_slope=slope), "relu": dict(act=L.ACT_RELU),
+          "leaky": dict(act=L.ACT_LEAKY, act_slope=0.01), "none": {}}[act]
+    F = torch.nn.functional
+    reff = {"prelu": lambda v: F.prelu(v, slope), "relu": F.relu, "leaky": lambda v: F.leaky_relu(v, 0.01),
+            "none": lambda v: v}[act]
+    ins = [x, w, b] + ([slope] if act == "prelu" else [])
+    o1, g1 = _grads(lambda: ops.linear([(x, None)], w, b, **kw), ins)
+    o2, g2 = _grads(lambda: reff(F.linear(x, w, b)), ins)
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < TOL[dtype] * 20
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_linear_autograd_broadcast_maps(dtype):
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(6, seed=22, mean_atoms=4.0)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV))
+    B, T, H = gr.B, 9, 32
+    en, gv = _leaf(_rand(B * T, H, dtype=dtype, seed=1)), _leaf(_rand(B, H, dtype=dtype, seed=2))
+    tab = _leaf(_rand(7, H // 2, dtype=dtype, seed=3))
+    w, b = _leaf(_rand(H, 2 * H + H // 2, dtype=dtype, seed=4, scale=0.2)), _leaf(_rand(H, dtype=dtype, seed=5))
+    sysid = g.system.to(DEV)
+
+    def mine():
+        pc = RowMap(div=T, div_rowptr=gr.token_rowptr(T))
+        ps = RowMap(idx=gr.system, div=T, div_rowptr=gr.token_rowptr(T), csr=gr.by_system)
+        return ops.linear([(en, None), (gv, pc), (tab, ps)], w, b, M=B * T, act=L.ACT_LEAKY, act_slope=0.01)
+
+    def ref():
+        cat = torch.cat([en, gv.repeat_interleave(T, 0), tab[sysid].repeat_interleave(T, 0)], 1)
+        return torch.nn.functional.leaky_relu(torch.nn.functional.linear(cat, w, b), 0.01)
+
+    o1, g1 = _grads(mine, [en, gv, tab, w, b])
+    o2, g2 = _grads(ref, [en, gv, tab, w, b])
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < TOL[dtype] * 20
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("W,prelu", [(32, False), (256, False), (512, True), (64, True), (1024, False)])
+def test_layer_norm(dtype, W, prelu):
+    M = 517
+    x = _leaf(_rand(M, W, dtype=dtype, seed=1, scale=2.0))
+    gam, bet = _leaf(_rand(W, dtype=dtype, seed=2)), _leaf(_rand(W, dtype=dtype, seed=3))
+    slope = _leaf(torch.tensor([0.25], dtype=dtype, device=DEV)) if prelu else None
+    ins = [x, gam, bet] + ([slope] if prelu else [])
+    F = torch.nn.functional
+
+    def ref():
+        y = F.layer_norm(x, (W,), gam, bet, 1e-5)
+        return F.prelu(y, slope) if prelu else y
+
+    o1, g1 = _grads(lambda: ops.layer_norm(x, gam, bet, slope), ins)
+    o2, g2 = _grads(ref, ins)
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < TOL[dtype] * 20
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("mean", [False, True])
+def test_segment_reduce(dtype, mean):
+    E, N, W = 4000, 300, 256
+    src = _leaf(_rand(E, W, dtype=dtype, seed=1))
+    key = torch.randint(0, N - 5, (E,), generator=torch.Generator().manual_seed(3))
+    key[:600] = 7                                                    # hub
+    csr, _ = ops.csr_build(ops.to_i32(key.to(DEV)), N)
+    kd = key.to(DEV)
+    o1, g1 = _grads(lambda: ops.segment_reduce(src, csr, mean), [src])
+    o2, g2 = _grads(lambda: (O.segment_mean if mean else O.segment_sum)(src, kd, N), [src])
+    assert relerr(o1[0], o2[0]) < TOL[dtype] * 20 and relerr(g1[0], g2[0]) < TOL[dtype] * 20
+    if not mean:   # same summation order as index_add_ on the CPU (ascending edge id): compare with a CPU run
+        cpu = O.segment_sum(src.detach().cpu(), key, N)
+        assert relerr(o1[0], cpu) < TOL[dtype]
+    # odd width / strided input path
+    src2 = _rand(E, 41, dtype=dtype, seed=2)
+    out2 = ops.segment_reduce_raw(src2[:, 3:40], csr.rowptr, csr.perm, N)
+    assert relerr(out2, O.segment_sum(src2[:, 3:40], kd, N)) < TOL[dtype] * 20
+
+
+def _dense_cross_ref(q, x_nodes, gam, bet, batch, H):
+    """The reference's padded formulation: to_dense_batch zero padding, LN on q and on padded keys, attention."""
+    dense, n, nmax = O.pad_crystals(x_nodes, batch)
+    F = torch.nn.functional
+    ln = lambda t: F.layer_norm(t, (H,), gam, bet, 1e-5)
+    return q + O.attention(ln(q), ln(dense))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("H,broadcast", [(32, False), (64, True), (256, False)])
+def test_cross_attention_matches_padded_reference(dtype, H, broadcast):
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(6, seed=31, mean_atoms=9.0, max_atoms=50)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV))
+    B, T = gr.B, 37
+    xn = _leaf(_rand(gr.N, H, dtype=dtype, seed=1))
+    q = _leaf(_rand(T, H, dtype=dtype, seed=2)) if broadcast else _leaf(_rand(B, T, H, dtype=dtype, seed=2))
+    gam, bet = _leaf(_rand(H, dtype=dtype, seed=3)), _leaf(_rand(H, dtype=dtype, seed=4))
+    bd = g.batch.to(DEV)
+
+    def mine():
+        kv = ops.layer_norm(xn, gam, bet)
+        ql = ops.layer_norm(q, gam, bet)
+        return ops.cross_attention(ql, kv, bet, q, gr, B)
+
+    def ref():
+        qq = q[None].expand(B, T, H) if broadcast else q
+        return _dense_cross_ref(qq, xn, gam, bet, bd, H)
+
+    o1, g1 = _grads(mine, [xn, q, gam, bet])
+    o2, g2 = _grads(ref, [xn, q, gam, bet])
+    tol = 5e-5 if dtype == torch.float32 else 5e-6        # fp32 softmax inside both paths
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_cross_attention_two_sequences_per_crystal(dtype):
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(4, seed=32, mean_atoms=5.0)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV))
+    B, T, H = gr.B, 20, 32
+    kv = _leaf(_rand(gr.N, H, dtype=dtype, seed=1))
+    ph = _leaf(_rand(H, dtype=dtype, seed=2))
+    q = _leaf(_rand(2 * B, T, H, dtype=dtype, seed=3))
+    o1, g1 = _grads(lambda: ops.cross_attention(q, kv, ph, q, gr, 2 * B), [kv, ph, q])
+
+    def ref():
+        dense, n, nmax = O.pad_crystals(kv, g.batch.to(DEV))
+        mask = torch.arange(nmax, device=DEV)[None, :] >= n[:, None]
+        dense = torch.where(mask[:, :, None], ph[None, None, :], dense)
+        dense2 = torch.cat([dense, dense], 0)
+        return q + O.attention(q, dense2)
+
+    o2, g2 = _grads(ref, [kv, ph, q])
+    tol = 5e-5 if dtype == torch.float32 else 5e-6
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("S,Lq,Lk,H", [(3, 51, 51, 32), (2, 201, 201, 256), (4, 17, 40, 64)])
+def test_dense_attention(dtype, S, Lq, Lk, H):
+    q, k = _leaf(_rand(S, Lq, H, dtype=dtype, seed=1)), _leaf(_rand(S, Lk, H, dtype=dtype, seed=2))
+    r = _leaf(_rand(S, Lq, H, dtype=dtype, seed=3))
+    o1, g1 = _grads(lambda: ops.self_attention(q, k, r), [q, k, r])
+    o2, g2 = _grads(lambda: r + O.attention(q, k), [q, k, r])
+    tol = 5e-5 if dtype == torch.float32 else 5e-6
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol
+    if Lq == Lk:    # same tensor as query and key (first self-attention layer)
+        o1, g1 = _grads(lambda: ops.self_attention(q, q, r), [q, r])
+        o2, g2 = _grads(lambda: r + O.attention(q, q), [q, r])
+        for a_, b_ in zip(o1 + g1, o2 + g2):
+            assert relerr(a_, b_) < tol
+
+
+def test_attention_dropout_properties():
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(4, seed=33, mean_atoms=12.0)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV))
+    B, T, H = gr.B, 64, 32
+    kv, ph, q = _rand(gr.N, H, seed=1), _rand(H, seed=2), _rand(B, T, H, seed=3)
+    zero = torch.zeros_like(q)
+    base = ops.cross_attention(q, kv, ph, zero, gr, B, 0.0, 0)
+    a = ops.cross_attention(q, kv, ph, zero, gr, B, 0.3, 1234)
+    b = ops.cross_attention(q, kv, ph, zero, gr, B, 0.3, 1234)
+    assert torch.equal(a, b)                                     # deterministic per seed
+    acc = torch.zeros_like(base)
+    n = 200
+    for s in range(n):
+        acc += ops.cross_attention(q, kv, ph, zero, gr, B, 0.3, 5000 + s)
+    assert relerr(acc / n, base) < 0.15                          # inverted dropout is unbiased
+    S, L_ = 3, 40
+    qq, kk = _rand(S, L_, H, seed=4), _rand(S, L_, H, seed=5)
+    z = torch.zeros_like(qq)
+    base = ops.self_attention(qq, kk, z)
+    acc = torch.zeros_like(base)
+    for s in range(n):
+        acc += ops.self_attention(qq, kk, z, 0.3, 7000 + s)
+    assert relerr(acc / n, base) < 0.15
+    # dropout backward is consistent with its forward (finite differences on a tiny case, fp64)
+    q64 = _leaf(_rand(1, 3, H, dtype=torch.float64, seed=6))
+    k64 = _rand(1, 5, H, dtype=torch.float64, seed=7)
+    out = ops.self_attention(q64, k64, torch.zeros_like(q64), 0.4, 42)
+    wgt = _rand(1, 3, H, dtype=torch.float64, seed=8)
+    (out * wgt).sum().backward()
+    eps = 1e-6
+    d = torch.zeros_like(q64)
+    d[0, 1, 3] = eps
+    with torch.no_grad():
+        f1 = (ops.self_attention(q64 + d, k64, torch.zeros_like(q64), 0.4, 42) * wgt).sum()
+        f0 = (ops.self_attention(q64 - d, k64, torch.zeros_like(q64), 0.4, 42) * wgt).sum()
+    assert abs(((f1 - f0) / (2 * eps)).item() - q64.grad[0, 1, 3].item()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("mode", ["edos", "phonon"])
+def test_loss(dtype, mode):
+    B, T = 37, 201 if mode == "edos" else 51
+    pg, ps = _leaf(_rand(B, T, dtype=dtype, seed=1).abs()), _leaf(_rand(B, T, dtype=dtype, seed=2).abs())
+    y = _rand(B * T, dtype=dtype, seed=3)
+    if mode == "phonon":
+        y = y.abs().view(B, T)
+    fn = O.edos_loss if mode == "edos" else O.phonon_loss
+    o1, g1 = _grads(lambda: ops.dos_loss(pg, ps, y, mode=mode, beta=0.7), [pg, ps])
+    o2, g2 = _grads(lambda: fn(pg, ps, y, 0.7), [pg, ps])
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < TOL[dtype] * 10
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_phonon_edge_features(dtype):
+    v = _rand(1000, 3, dtype=dtype, seed=1, scale=2.5)
+    v[::7] = 0
+    out = ops.phonon_edge_features(v)
+    assert relerr(out, O.phonon_edge_features(v.double().cpu())) < TOL[dtype] * 10
+
+
+def test_colsum_and_determinism():
+    x = _rand(20000, 1024, seed=1)
+    a, b = ops.colsum(x), ops.colsum(x)
+    assert torch.equal(a, b) and relerr(a, x.double().sum(0)) < 1e-5
+    y = _rand(64, 51456, seed=2)
+    assert relerr(ops.colsum(y), y.double().sum(0)) < 1e-5
