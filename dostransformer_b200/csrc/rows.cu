@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_kernel(const T* __restr
   }
   const bool has_act = slope_p != nullptr;
   const T slope = has_act ? __ldg(slope_p) : T(0);
-  T dsl = T(0);
+  double dsl = 0.0;  // the PReLU slope gradient is one scalar summed over M*W terms: accumulate it in fp64
   const T invW = T(1) / T(W);
   const long long rbeg = blockIdx.x * rows_per_block;
   const long long rend = min(M, rbeg + rows_per_block);
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_kernel(const T* __restr
         if (has_act) {
           const T o = xh[i] * gam[i] + bet[i];
           if (!(o > T(0))) {
-            dsl += g * o;
+            dsl += (double)g * (double)o;
             g *= slope;
           }
         }
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_kernel(const T* __restr
     }
   }
   dsl = warp_sum(dsl);
-  if (lane == 0) red[warp] = dsl;
+  if (lane == 0) red[warp] = (T)dsl;
   __syncthreads();
   T* wsb = ws + (long long)blockIdx.x * (2 * W + 1);
   for (int c = threadIdx.x; c < 2 * W; c += blockDim.x) {
@@ -233,27 +233,27 @@ template <typename T>
 __global__ void __launch_bounds__(256) prelu_bwd_kernel(const T* __restrict__ da, const T* __restrict__ z,
                                                         const T* __restrict__ slope_p, T* __restrict__ dz,
                                                         T* __restrict__ ws, long long n, long long per_block) {
-  __shared__ T red[8];
+  __shared__ double red[8];
   const T slope = __ldg(slope_p);
   const long long beg = blockIdx.x * per_block, end = min(n, beg + per_block);
-  T acc = T(0);
+  double acc = 0.0;
   for (long long i = beg + threadIdx.x; i < end; i += blockDim.x) {
     const T zz = z[i], g = da[i];
     if (zz > T(0)) {
       dz[i] = g;
     } else {
       dz[i] = g * slope;
-      acc += g * zz;
+      acc += (double)g * (double)zz;
     }
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    T s = T(0);
+    double s = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w];
-    ws[blockIdx.x] = s;
+    ws[blockIdx.x] = (T)s;
   }
 }
 

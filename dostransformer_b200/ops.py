@@ -146,7 +146,7 @@ def gemm_raw(*, M: int, N: int, K: int, a: Sequence[Tuple[torch.Tensor, Optional
     g.M, g.N, g.K, g.batch = M, N, K, batch
     g.a_mode, g.a_nseg = a_mode, len(a)
     for i, (t, m) in enumerate(a):
-        width = t.shape[-1] if a_mode == L.KC else K
+        width = t.shape[-1] if (a_mode == L.KC and len(a) > 1) else K
         g.a[i] = _seg(t if t.dim() == 2 else t.reshape(-1, t.shape[-1]), m, width)
         if lda is not None:
             g.a[i].ld = lda

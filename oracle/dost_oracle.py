@@ -38,14 +38,16 @@ def segment_mean(src: torch.Tensor, index: torch.Tensor, size: int) -> torch.Ten
     return segment_sum(src, index, size) / cnt[:, None]
 
 
-def pad_crystals(x: torch.Tensor, batch: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+def pad_crystals(x: torch.Tensor, batch: torch.Tensor, max_num_nodes: Optional[int] = None
+                 ) -> Tuple[torch.Tensor, torch.Tensor, int]:
     """torch_geometric.utils.to_dense_batch -- DOSTransformer.py:61.  Returns
-    ([B, Nmax, H] zero padded, atoms per crystal, Nmax)."""
+    ([B, Nmax, H] zero padded, atoms per crystal, Nmax).  ``max_num_nodes`` is PyG's argument of the same name
+    (the reference never passes it; the data-parallel tests use it to impose the global padding length)."""
     B = int(batch.max()) + 1
     n = torch.bincount(batch, minlength=B)
-    nmax = int(n.max())
+    nmax = int(n.max()) if max_num_nodes is None else int(max_num_nodes)
     start = torch.cumsum(n, 0) - n
-    slot = torch.arange(batch.numel()) - start[batch] + batch * nmax
+    slot = torch.arange(batch.numel(), device=batch.device) - start[batch] + batch * nmax
     dense = x.new_zeros(B * nmax, x.shape[1])
     dense[slot] = x
     return dense.view(B, nmax, x.shape[1]), n, nmax
@@ -121,10 +123,11 @@ def _message_passing(p: Params, x, e, row, col, n_layers: int, mean: bool):
     return x, e
 
 
-def _dos_heads(p: Params, x, batch, system, energies_tok, graph, prompt_name, t_layers, drop_p, training):
+def _dos_heads(p: Params, x, batch, system, energies_tok, graph, prompt_name, t_layers, drop_p, training,
+               max_num_nodes=None):
     """Everything after the GNN -- DOSTransformer.py:61-91 / DOSTransformer_phonon.py:86-117."""
     T = energies_tok.shape[0]
-    dense, n, nmax = pad_crystals(x, batch)                     # [B, Nmax, H]; padded rows are zero
+    dense, n, nmax = pad_crystals(x, batch, max_num_nodes)      # [B, Nmax, H]; padded rows are zero
     B = dense.shape[0]
     q0 = energies_tok[None].expand(B, T, -1)
     energies = encoder_stack(p, "transformer", q0, dense, t_layers, drop_p, training)
@@ -141,7 +144,7 @@ def _dos_heads(p: Params, x, batch, system, energies_tok, graph, prompt_name, t_
     return dos_global, dos_system
 
 
-def edos_forward(p: Params, g, *, training: bool = False, attn_drop: float = 0.0):
+def edos_forward(p: Params, g, *, training: bool = False, attn_drop: float = 0.0, max_num_nodes=None):
     """DOSTransformer.forward -- embedder_eDOS/DOSTransformer.py:45-93.
     Returns (dos_global [B,T], x [N,H], dos_system [B,T])."""
     L = len({k.split(".")[1] for k in p if k.startswith("stacked_processor.")})
@@ -155,11 +158,11 @@ def edos_forward(p: Params, g, *, training: bool = False, attn_drop: float = 0.0
     pooled = segment_sum(x, g.batch, B)
     graph = _lin(p, "GN_decoder.mlp.0", torch.cat([u, pooled], dim=1))       # Decoder :156-161
     dg, ds = _dos_heads(p, x, g.batch, g.system, p["embeddings.weight"], graph, "promt_token", t,
-                        attn_drop, training)
+                        attn_drop, training, max_num_nodes)
     return dg, x, ds
 
 
-def phonon_forward(p: Params, g, *, training: bool = False, attn_drop: float = 0.0):
+def phonon_forward(p: Params, g, *, training: bool = False, attn_drop: float = 0.0, max_num_nodes=None):
     """DOSTransformer_phonon.forward -- embedder_phDOS/DOSTransformer_phonon.py:66-119."""
     L = len({k.split(".")[1] for k in p if k.startswith("stacked_processor.")})
     t = len({k.split(".")[2] for k in p if k.startswith("transformer.layers.")})
@@ -171,7 +174,7 @@ def phonon_forward(p: Params, g, *, training: bool = False, attn_drop: float = 0
     B = int(g.batch.max()) + 1
     graph = _lin(p, "GN_decoder.mlp.0", segment_sum(x, g.batch, B))          # Decoder :178-183
     dg, ds = _dos_heads(p, x, g.batch, g.system, p["embeddings.weight"], graph, "prompt_token", t,
-                        attn_drop, training)
+                        attn_drop, training, max_num_nodes)
     return dg, x, ds
 
 

@@ -26,15 +26,24 @@ def _step(model, g, mode, beta=1.0):
     return dg.detach(), x.detach(), ds.detach(), loss.detach(), grads
 
 
+def _rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
 def _check_grads(grads, ref32, ref64, floor=1e-4):
+    """Per tensor, against the fp64 arbiter: relative L2 error < max(1e-4, 3 x the reference's own fp32-vs-fp64 L2 noise)
+    and max-norm error < max(3e-4, 3 x its max-norm noise).  ReLU/PReLU gate flips make single entries of an fp32
+    gradient differ at the 1e-4..1e-3 level between ANY two fp32 evaluation orders (SURVEY.md 8c calibration), which is
+    why the max-norm bound is the looser of the two."""
     assert set(grads) == set(ref64)
     bad = []
     for k, r64 in ref64.items():
-        noise = relerr(ref32[k], r64) if ref32 is not None else 0.0
-        tol = max(floor, 3 * noise)
-        err = relerr(grads[k], r64)
-        if not err < tol:
-            bad.append((k, err, tol))
+        n_inf = relerr(ref32[k], r64) if ref32 is not None else 0.0
+        n_l2 = _rel_l2(ref32[k], r64) if ref32 is not None else 0.0
+        e_inf, e_l2 = relerr(grads[k], r64), _rel_l2(grads[k], r64)
+        if not (e_l2 < max(floor, 3 * n_l2) and e_inf < max(3 * floor, 3 * n_inf)):
+            bad.append((k, e_l2, n_l2, e_inf, n_inf))
     assert not bad, bad
 
 
@@ -155,7 +164,8 @@ def test_transformer_encoder_module_matches_oracle():
     x = torch.randn(21, 3, 64)
     kv = torch.randn(33, 3, 64)
     ref = O.encoder_stack(sd, "t", x.transpose(0, 1), kv.transpose(0, 1), 2).transpose(0, 1)
-    out = enc(x.to(DEV), kv.to(DEV), kv.to(DEV))
+    kvd = kv.to(DEV)
+    out = enc(x.to(DEV), kvd, kvd)
     assert out.shape == ref.shape and relerr(out, ref) < 1e-4
     ref_self = O.encoder_stack(sd, "t", x.transpose(0, 1), x.transpose(0, 1), 2).transpose(0, 1)
     xs = x.to(DEV)

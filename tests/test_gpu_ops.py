@@ -365,13 +365,13 @@ def test_attention_dropout_properties():
     out = ops.self_attention(q64, k64, torch.zeros_like(q64), 0.4, 42)
     wgt = _rand(1, 3, H, dtype=torch.float64, seed=8)
     (out * wgt).sum().backward()
-    eps = 1e-6
+    eps = 1e-3          # the softmax inside is fp32 (reference quirk): finite differences need a coarse step
     d = torch.zeros_like(q64)
     d[0, 1, 3] = eps
     with torch.no_grad():
         f1 = (ops.self_attention(q64 + d, k64, torch.zeros_like(q64), 0.4, 42) * wgt).sum()
         f0 = (ops.self_attention(q64 - d, k64, torch.zeros_like(q64), 0.4, 42) * wgt).sum()
-    assert abs(((f1 - f0) / (2 * eps)).item() - q64.grad[0, 1, 3].item()) < 1e-5
+    assert abs(((f1 - f0) / (2 * eps)).item() - q64.grad[0, 1, 3].item()) < 2e-3
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
