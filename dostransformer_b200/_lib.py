@@ -17,6 +17,8 @@ LIB_PATH = os.path.join(_HERE, "libdost_b200.so")
 F32, F64 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_PRELU = 0, 1, 2, 3
 KC, MC = 0, 1
+PREC_FMA, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FMA, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 _lib: Optional[C.CDLL] = None
 
@@ -36,7 +38,7 @@ class Gemm(C.Structure):
         ("dact_saved", C.c_void_p), ("ld_dact", C.c_longlong), ("dact_kind", C.c_int), ("dact_slope", C.c_double),
         ("residual", C.c_void_p), ("ld_res", C.c_longlong),
         ("out", C.c_void_p), ("ldc", C.c_longlong), ("c_bstride", C.c_longlong),
-        ("accumulate", C.c_int), ("split_k", C.c_int),
+        ("accumulate", C.c_int), ("split_k", C.c_int), ("precision", C.c_int),
     ]
 
 
@@ -102,7 +104,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 1:
+    if lib.dost_abi_version() != 2:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib

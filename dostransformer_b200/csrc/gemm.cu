@@ -11,48 +11,9 @@
 // Tile: (16*TM) x (16*TN) x 16 with TM = TN = 2 * (16 bytes / sizeof(T)); 256 threads; each thread owns a
 // 2x2 arrangement of VxV sub-tiles (bank-conflict-free vector reads of the shared tiles); global loads are
 // register-staged one k-tile ahead of the math (double-buffered shared memory, one barrier per k-tile).
-#include "common.cuh"
+#include "gemm_common.cuh"
 
 namespace dost {
-
-template <typename T>
-struct SegDev {
-  const T* base;
-  long long ld;
-  const int* idx;
-  int div;
-  int kend;    // cumulative end of this segment along k
-  int vec_ok;  // 16-byte vector loads allowed
-};
-
-template <typename T>
-struct GemmDev {
-  int M, N, K;
-  int a_nseg;
-  SegDev<T> a[3];
-  long long a_bstride;
-  SegDev<T> b;
-  long long b_bstride;
-  const T* bias;
-  int act;
-  T act_slope;
-  const T* prelu_slope;
-  T* out_pre;
-  long long ld_pre;
-  const T* dact_saved;
-  long long ld_dact;
-  T dact_slope;
-  const T* residual;
-  long long ld_res;
-  T* out;
-  long long ldc;
-  long long c_bstride;
-  int accumulate;
-  int zmode;  // 0: single, 1: batched over blockIdx.z, 2: split-K over blockIdx.z (raw partials to ws)
-  int kchunk;
-  T* ws;
-  int epi_vec;
-};
 
 template <typename T> __device__ __forceinline__ typename VecOf<T>::type vzero();
 template <> __device__ __forceinline__ float4 vzero<float>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
@@ -352,6 +313,16 @@ __global__ void splitk_reduce_kernel(const T* __restrict__ ws, T* __restrict__ o
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// precision: 0 = FMA pipe (fp32/fp64), 1 = tcgen05 bf16x3 (fp32 parity), 2 = tcgen05 bf16.
+static inline bool use_tensor_cores(const GemmDev<float>& g, int precision, bool amc, bool bmc) {
+  return precision > 0 && gemm_tc_supported(g, amc, bmc);
+}
+static inline bool use_tensor_cores(const GemmDev<double>&, int, bool, bool) { return false; }
+static inline int launch_tc(const GemmDev<float>& g, int precision, bool amc, bool bmc, int batch, int split, cudaStream_t st) {
+  return launch_gemm_tc(g, precision, amc, bmc, batch, split, st);
+}
+static inline int launch_tc(const GemmDev<double>&, int, bool, bool, int, int, cudaStream_t) { return DOST_ERR_UNSUPPORTED; }
+
 template <typename T>
 static int run_gemm(const dost_gemm_t* h, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   constexpr int V = VecOf<T>::N;
@@ -363,6 +334,7 @@ static int run_gemm(const dost_gemm_t* h, void* workspace, size_t workspace_byte
   DOST_REQUIRE(h->M > 0 && h->N > 0 && h->K >= 0, "gemm: bad shape M=%d N=%d K=%d", h->M, h->N, h->K);
   DOST_REQUIRE(!(batch > 1 && split > 1), "gemm: batch and split_k are exclusive");
   DOST_REQUIRE(h->out != nullptr, "gemm: out is null");
+  DOST_REQUIRE(h->precision >= 0 && h->precision <= 2, "gemm: precision must be 0 (FMA), 1 (bf16x3) or 2 (bf16)");
   g.a_nseg = (h->a_mode == DOST_MC) ? 1 : h->a_nseg;
   DOST_REQUIRE(g.a_nseg >= 1 && g.a_nseg <= 3, "gemm: a_nseg must be 1..3");
   int kacc = 0;
@@ -429,14 +401,19 @@ static int run_gemm(const dost_gemm_t* h, void* workspace, size_t workspace_byte
     g.ws = (T*)workspace;
     gz = split;
   }
-  dim3 grid(ceil_div(h->M, BM), ceil_div(h->N, BN), gz);
-  DOST_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large");
   const bool amc = h->a_mode == DOST_MC, bmc = h->b_mode == DOST_MC;
-  if (amc && bmc) gemm_kernel<T, true, true><<<grid, 256, 0, st>>>(g);
-  else if (amc) gemm_kernel<T, true, false><<<grid, 256, 0, st>>>(g);
-  else if (bmc) gemm_kernel<T, false, true><<<grid, 256, 0, st>>>(g);
-  else gemm_kernel<T, false, false><<<grid, 256, 0, st>>>(g);
-  int rc = check_launch("gemm");
+  int rc;
+  if (use_tensor_cores(g, h->precision, amc, bmc)) {
+    rc = launch_tc(g, h->precision, amc, bmc, batch, split, st);
+  } else {
+    dim3 grid(ceil_div(h->M, BM), ceil_div(h->N, BN), gz);
+    DOST_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm: grid too large");
+    if (amc && bmc) gemm_kernel<T, true, true><<<grid, 256, 0, st>>>(g);
+    else if (amc) gemm_kernel<T, true, false><<<grid, 256, 0, st>>>(g);
+    else if (bmc) gemm_kernel<T, false, true><<<grid, 256, 0, st>>>(g);
+    else gemm_kernel<T, false, false><<<grid, 256, 0, st>>>(g);
+    rc = check_launch("gemm");
+  }
   if (rc != DOST_OK) return rc;
   if (split > 1) {
     const long long total = (long long)h->M * h->N;

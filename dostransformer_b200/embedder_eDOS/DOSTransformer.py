@@ -5,6 +5,8 @@ seeded initial weights; every device op is a kernel of libdost_b200.so (sm_100a)
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -14,12 +16,13 @@ from .. import ops
 
 class DOSTransformer(nn.Module):
     def __init__(self, layers, t_layers, n_atom_feats, n_bond_feats, n_glob_feats, n_hidden, device, attn_drop=0.0,
-                 *, n_energies: int = 201):
+                 *, n_energies: int = 201, precision: str = None):
         super().__init__()
         if n_hidden % 32 != 0 or n_hidden > 512:
             raise ValueError("dostransformer_b200 kernels need n_hidden in {32, 64, 128, 256, 512}")
         h = n_hidden
         self.n_energies = n_energies
+        self.precision = precision or os.environ.get("DOST_PRECISION", "fp32")   # fp32 | bf16x3 | bf16 (ops.py)
         self.attn_drop = float(attn_drop)
         # creation order == RNG order of the reference (DOSTransformer.py:17-42)
         self.embeddings = nn.Embedding(n_energies, h)
@@ -39,6 +42,10 @@ class DOSTransformer(nn.Module):
         self.max_num_nodes = None      # data-parallel: global padding length (phantom-key count) set by the sharder
 
     def forward(self, g):
+        with ops.precision(self.precision):
+            return self._forward(g)
+
+    def _forward(self, g):
         K.require_cuda(self.fc.weight, "the model")
         K.require_cuda(g.x, "the batch")
         graph = ops.build_graph(g.edge_index, g.batch, g.system, nmax_override=self.max_num_nodes,

@@ -6,6 +6,8 @@ global features, T = 51.  Runs in the dtype of its parameters (float64 under mai
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -19,7 +21,7 @@ def _looks_like_device(v):
 
 class DOSTransformer_phonon(nn.Module):
     def __init__(self, layers, t_layers, n_atom_feats, n_bond_feats, n_hidden, device=None, attn_drop=0.0,
-                 *, n_energies: int = 51):
+                 *, n_energies: int = 51, precision: str = None):
         super().__init__()
         # main_phDOS.py:68 calls (..., n_hidden, out_dim, device): the declared (device, attn_drop) slots then hold
         # (out_dim:int, device).  Accept both orders.
@@ -29,6 +31,7 @@ class DOSTransformer_phonon(nn.Module):
             raise ValueError("dostransformer_b200 kernels need n_hidden in {32, 64, 128, 256, 512}")
         h = n_hidden
         self.n_energies = n_energies
+        self.precision = precision or os.environ.get("DOST_PRECISION", "fp32")   # fp32 | bf16x3 | bf16 (ops.py)
         self.attn_drop = float(attn_drop)
         # creation order == RNG order of the reference (DOSTransformer_phonon.py:19-43)
         self.embeddings = nn.Embedding(n_energies, h)
@@ -48,6 +51,10 @@ class DOSTransformer_phonon(nn.Module):
         self.max_num_nodes = None
 
     def forward(self, g):
+        with ops.precision(self.precision):
+            return self._forward(g)
+
+    def _forward(self, g):
         K.require_cuda(self.fc.weight, "the model")
         K.require_cuda(g.x, "the batch")
         if "edge_index" not in g:

@@ -17,6 +17,36 @@ from . import _lib as L
 
 NUM_SMS = 148
 
+# GEMM precision: "fp32" = FMA pipe (bit-for-bit fp32 arithmetic), "bf16x3" = tcgen05 tensor cores with error-compensated
+# bf16 operand splits (fp32 parity), "bf16" = tcgen05 with bf16 operands (fp32 accumulate; stated looser tolerance).
+_PRECISION = L.PREC_FMA
+
+
+def set_precision(name: str) -> None:
+    global _PRECISION
+    _PRECISION = L.PRECISIONS[name]
+
+
+def get_precision() -> int:
+    return _PRECISION
+
+
+class precision:
+    """Context manager: ``with ops.precision("bf16x3"): ...``"""
+
+    def __init__(self, name: str):
+        self.new = L.PRECISIONS[name]
+
+    def __enter__(self):
+        global _PRECISION
+        self.old, _PRECISION = _PRECISION, self.new
+        return self
+
+    def __exit__(self, *exc):
+        global _PRECISION
+        _PRECISION = self.old
+        return False
+
 
 def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
@@ -140,7 +170,8 @@ def gemm_raw(*, M: int, N: int, K: int, a: Sequence[Tuple[torch.Tensor, Optional
              dact_saved: Optional[torch.Tensor] = None, dact_kind: int = L.ACT_NONE, dact_slope: float = 0.0,
              residual: Optional[torch.Tensor] = None, accumulate: bool = False, split_k: int = 1,
              batch: int = 1, a_bstride: int = 0, b_bstride: int = 0, c_bstride: int = 0,
-             ldb: Optional[int] = None, ldc: Optional[int] = None, lda: Optional[int] = None) -> None:
+             ldb: Optional[int] = None, ldc: Optional[int] = None, lda: Optional[int] = None,
+             prec: Optional[int] = None) -> None:
     g = L.Gemm()
     g.dtype = L.dt(out)
     g.M, g.N, g.K, g.batch = M, N, K, batch
@@ -171,6 +202,7 @@ def gemm_raw(*, M: int, N: int, K: int, a: Sequence[Tuple[torch.Tensor, Optional
     g.c_bstride = c_bstride
     g.accumulate = 1 if accumulate else 0
     g.split_k = split_k
+    g.precision = _PRECISION if prec is None else prec
     lib = L.lib()
     ws, nb = None, 0
     if split_k > 1:
@@ -250,6 +282,7 @@ class _Linear(torch.autograd.Function):
         gemm_raw(M=M, N=N, K=K, a=segs, a_mode=L.KC, b=weight, b_mode=L.KC, out=out, bias=bias, act=spec.act,
                  act_slope=spec.act_slope, prelu_slope=slope, out_pre=pre, residual=residual)
         ctx.spec = spec
+        ctx.prec = _PRECISION
         ctx.n_tensors = len(tensors)
         ctx.has_bias, ctx.has_res = bias is not None, residual is not None
         saved_act = None
@@ -312,14 +345,14 @@ class _Linear(torch.autograd.Function):
                 w = t.shape[-1]
                 split = _pick_split(N, w, M, weight.element_size())
                 gemm_raw(M=N, N=w, K=M, a=[(dv, None)], a_mode=L.MC, b=t, b_mode=L.MC, b_map=spec.maps[si],
-                         out=d_weight[:, k0:k0 + w], ldc=K, split_k=split)
+                         out=d_weight[:, k0:k0 + w], ldc=K, split_k=split, prec=ctx.prec)
                 k0 += w
         # ---- inputs: dA = dv @ W  [M, K], then the adjoint of each row map
         d_tensors: List[Optional[torch.Tensor]] = [None] * ctx.n_tensors
         tens_needs = needs[5:]
         if any(tens_needs):
             dA = torch.empty(M, K, dtype=dtype, device=dev)
-            gemm_raw(M=M, N=K, K=N, a=[(dv, None)], a_mode=L.KC, b=weight, b_mode=L.MC, out=dA)
+            gemm_raw(M=M, N=K, K=N, a=[(dv, None)], a_mode=L.KC, b=weight, b_mode=L.MC, out=dA, prec=ctx.prec)
             k0 = 0
             for si, ti in enumerate(spec.tensor_of_seg):
                 t = tensors[ti]
@@ -540,7 +573,7 @@ class _SelfAttention(torch.autograd.Function):
         gemm_raw(M=Lq, N=H, K=Lk, a=[(pd.view(S * Lq, Lp), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.MC,
                  out=out, residual=resid, batch=S, a_bstride=Lq * Lp, b_bstride=Lk * H, c_bstride=Lq * H, ldc=H, lda=Lp)
         ctx.save_for_backward(q, k, scores, pd if drop_p > 0 else None)
-        ctx.drop_p, ctx.seed = drop_p, seed
+        ctx.drop_p, ctx.seed, ctx.prec = drop_p, seed, _PRECISION
         return out
 
     @staticmethod
@@ -556,20 +589,21 @@ class _SelfAttention(torch.autograd.Function):
         # dPd = dO k^T
         dpd = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
         gemm_raw(M=Lq, N=Lk, K=H, a=[(d_out.view(S * Lq, H), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.KC,
-                 out=dpd, batch=S, a_bstride=Lq * H, b_bstride=Lk * H, c_bstride=Lq * Lp, ldc=Lp)
+                 out=dpd, batch=S, a_bstride=Lq * H, b_bstride=Lk * H, c_bstride=Lq * Lp, ldc=Lp, prec=ctx.prec)
         ds = dpd  # in place
         L.check(L.lib().dost_softmax_bwd(L.dt(q), L.p(prob), L.p(dpd), L.p(ds), S * Lq, Lk, Lp, scale, ctx.drop_p,
                                          ctx.seed, L.stream()), "softmax_bwd")
         # dQ = dS k
         dq = torch.empty(S, Lq, H, dtype=dtype, device=dev)
         gemm_raw(M=Lq, N=H, K=Lk, a=[(ds.view(S * Lq, Lp), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.MC,
-                 out=dq, batch=S, a_bstride=Lq * Lp, b_bstride=Lk * H, c_bstride=Lq * H, ldc=H, lda=Lp)
+                 out=dq, batch=S, a_bstride=Lq * Lp, b_bstride=Lk * H, c_bstride=Lq * H, ldc=H, lda=Lp, prec=ctx.prec)
         # dK = dS^T q + Pd^T dO   (reduction over the Lq queries)
         dk = torch.empty(S, Lk, H, dtype=dtype, device=dev)
         gemm_raw(M=Lk, N=H, K=Lq, a=[(ds.view(S * Lq, Lp), None)], a_mode=L.MC, b=q.view(S * Lq, H), b_mode=L.MC,
-                 out=dk, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp)
+                 out=dk, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp, prec=ctx.prec)
         gemm_raw(M=Lk, N=H, K=Lq, a=[(pd.view(S * Lq, Lp), None)], a_mode=L.MC, b=d_out.view(S * Lq, H), b_mode=L.MC,
-                 out=dk, accumulate=True, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp)
+                 out=dk, accumulate=True, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp,
+                 prec=ctx.prec)
         return dq, dk, d_out, None, None
 
 

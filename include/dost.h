@@ -27,11 +27,12 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 1
+#define DOST_ABI_VERSION 2
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
 enum { DOST_ACT_NONE = 0, DOST_ACT_RELU = 1, DOST_ACT_LEAKY = 2, DOST_ACT_PRELU = 3 };
+enum { DOST_PREC_FMA = 0, DOST_PREC_BF16X3 = 1 /* error-compensated, fp32 parity */, DOST_PREC_BF16 = 2 };
 enum { DOST_KC = 0 /* reduction index contiguous */, DOST_MC = 1 /* row/col index contiguous */ };
 
 typedef void* dost_stream_t; /* cudaStream_t */
@@ -57,7 +58,7 @@ int dost_csr_build(const int32_t* key, long long n, long long size, int32_t* row
                    int32_t* maxcount, void* workspace, size_t workspace_bytes, dost_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * GEMM family (fp32/fp64 FMA path).  C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ).
+ * GEMM family (fp32/fp64 FMA pipe, or tcgen05 tensor cores for fp32 data).  C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ).
  * Replaces nn.Linear / torch.bmm / torch.cat / x[row] / .repeat on the path:
  * DOSTransformer.py:103-105,116-120 (encoders), :139-143,174-175 (gather+cat+edge_mlp), :188-190
  * (node_mlp_2), :65-69,79-83 (repeat+cat+fc/fc_prompt), :75,89 (out_layer), :158-159 (decoder);
@@ -97,6 +98,8 @@ typedef struct {
   void* out; long long ldc; long long c_bstride;
   int accumulate;            /* out += v instead of out = v */
   int split_k;               /* >= 1; > 1 needs workspace of split_k*M*N elements, reduced in fixed order */
+  int precision;             /* DOST_PREC_*: FMA pipe, or tcgen05 tensor cores with bf16x3 / bf16 operands (F32 only;
+                                problems too small for a 128 x N tile stay on the FMA pipe) */
 } dost_gemm_t;
 
 size_t dost_gemm_workspace_bytes(const dost_gemm_t* g);

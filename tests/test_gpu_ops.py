@@ -403,3 +403,103 @@ def test_colsum_and_determinism():
     assert torch.equal(a, b) and relerr(a, x.double().sum(0)) < 1e-5
     y = _rand(64, 51456, seed=2)
     assert relerr(ops.colsum(y), y.double().sum(0)) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------- tcgen05 GEMM
+TC_TOL = {"bf16x3": 2e-5, "bf16": 2e-2}
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (1000, 512, 768), (333, 70, 200), (4096, 1024, 256), (128, 64, 64),
+                                   (513, 201, 256), (130, 256, 41)])
+def test_tc_gemm_forward_shapes(prec, M, N, K):
+    a, w, b = _rand(M, K, seed=1), _rand(N, K, seed=2), _rand(N, seed=3)
+    res = _rand(M, N, seed=4)
+    out = torch.empty(M, N, device=DEV)
+    pre = torch.empty(M, N, device=DEV)
+    slope = torch.tensor([0.25], device=DEV)
+    ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=out, bias=b, act=L.ACT_PRELU,
+                 prelu_slope=slope, out_pre=pre, residual=res, prec=L.PRECISIONS[prec])
+    v = a.double() @ w.double().T + b.double()
+    ref = torch.nn.functional.prelu(v, slope.double()) + res.double()
+    assert relerr(pre, v) < TC_TOL[prec], relerr(pre, v)
+    assert relerr(out, ref) < TC_TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+def test_tc_gemm_modes_splitk_batched(prec):
+    P = L.PRECISIONS[prec]
+    tol = TC_TOL[prec]
+    M, N, K = 1500, 256, 512
+    dy, x, w = _rand(M, N, seed=1), _rand(M, K, seed=2), _rand(N, K, seed=3)
+    dx = torch.empty(M, K, device=DEV)
+    ops.gemm_raw(M=M, N=K, K=N, a=[(dy, None)], a_mode=L.KC, b=w, b_mode=L.MC, out=dx, prec=P)       # B MN-major
+    assert relerr(dx, dy.double() @ w.double()) < tol
+    dw = torch.zeros(N, K + 64, device=DEV)
+    for split in (1, 4):
+        ops.gemm_raw(M=N, N=K, K=M, a=[(dy, None)], a_mode=L.MC, b=x, b_mode=L.MC, out=dw[:, 64:], ldc=K + 64,
+                     split_k=split, prec=P)                                                           # A and B MN-major
+        assert relerr(dw[:, 64:], dy.double().T @ x.double()) < tol
+        assert dw[:, :64].abs().max() == 0
+    idx = torch.randint(0, 300, (M,), dtype=torch.int32, device=DEV)
+    xs = _rand(300, K, seed=5)
+    dw2 = torch.empty(N, K, device=DEV)
+    ops.gemm_raw(M=N, N=K, K=M, a=[(dy, None)], a_mode=L.MC, b=xs, b_mode=L.MC, b_map=RowMap(idx=idx), out=dw2, split_k=3,
+                 prec=P)
+    assert relerr(dw2, dy.double().T @ xs.double()[idx.long()]) < tol
+    # A MN-major with B K-major
+    at = _rand(K, M, seed=6)          # A(m,k) = at[k, m]
+    o = torch.empty(M, N, device=DEV)
+    ops.gemm_raw(M=M, N=N, K=K, a=[(at, None)], a_mode=L.MC, b=w, b_mode=L.KC, out=o, prec=P)
+    assert relerr(o, at.double().T @ w.double().T) < tol
+    # gathered, concatenated A (edge-MLP shape) and broadcast rows
+    E, Nn, H = 3000, 200, 256
+    xn, e = _rand(Nn, H, seed=7), _rand(E, H, seed=8)
+    w3 = _rand(2 * H, 3 * H, seed=9, scale=0.1)
+    row = torch.randint(0, Nn, (E,), dtype=torch.int32, device=DEV)
+    col = torch.randint(0, Nn, (E,), dtype=torch.int32, device=DEV)
+    o3 = torch.empty(E, 2 * H, device=DEV)
+    ops.gemm_raw(M=E, N=2 * H, K=3 * H, a=[(xn, RowMap(idx=row)), (xn, RowMap(idx=col)), (e, None)], a_mode=L.KC, b=w3,
+                 b_mode=L.KC, out=o3, prec=P)
+    cat = torch.cat([xn[row.long()], xn[col.long()], e], 1).double()
+    assert relerr(o3, cat @ w3.double().T) < tol
+    # batched attention shapes with padded leading dimension
+    S, T2, H2 = 6, 201, 256
+    q, k = _rand(S, T2, H2, seed=10), _rand(S, T2, H2, seed=11)
+    Tp = 204
+    sc = torch.zeros(S, T2, Tp, device=DEV)
+    ops.gemm_raw(M=T2, N=T2, K=H2, a=[(q.view(-1, H2), None)], a_mode=L.KC, b=k.view(-1, H2), b_mode=L.KC, out=sc, batch=S,
+                 a_bstride=T2 * H2, b_bstride=T2 * H2, c_bstride=T2 * Tp, ldc=Tp, prec=P)
+    assert relerr(sc[:, :, :T2], torch.bmm(q.double(), k.double().transpose(1, 2))) < tol
+    assert sc[:, :, T2:].abs().max() == 0
+    pv = torch.empty(S, T2, H2, device=DEV)
+    ops.gemm_raw(M=T2, N=H2, K=T2, a=[(sc.view(-1, Tp), None)], a_mode=L.KC, b=k.view(-1, H2), b_mode=L.MC, out=pv, batch=S,
+                 a_bstride=T2 * Tp, b_bstride=T2 * H2, c_bstride=T2 * H2, ldc=H2, lda=Tp, prec=P)
+    assert relerr(pv, torch.bmm(sc[:, :, :T2].double(), k.double())) < tol
+    dk = torch.empty(S, T2, H2, device=DEV)
+    ops.gemm_raw(M=T2, N=H2, K=T2, a=[(sc.view(-1, Tp), None)], a_mode=L.MC, b=q.view(-1, H2), b_mode=L.MC, out=dk, batch=S,
+                 a_bstride=T2 * Tp, b_bstride=T2 * H2, c_bstride=T2 * H2, ldc=H2, lda=Tp, prec=P)
+    assert relerr(dk, torch.bmm(sc[:, :, :T2].double().transpose(1, 2), q.double())) < tol
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
+def test_tc_model_matches_fp32_path(prec, tol):
+    from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+    from dostransformer_b200.synthetic import make_edos_batch
+    torch.manual_seed(0)
+    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device(DEV), 0.0).to(DEV)
+    g = make_edos_batch(24, seed=77).to(DEV)
+
+    def run(p):
+        m.precision = p
+        m.zero_grad(set_to_none=True)
+        dg, x, ds = m(g)
+        loss = ops.dos_loss(dg, ds, g.y_ft, mode="edos")
+        loss.backward()
+        return dg.detach(), ds.detach(), loss.detach(), {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}
+
+    a, b = run("fp32"), run(prec)
+    assert relerr(b[0], a[0]) < tol and relerr(b[1], a[1]) < tol
+    assert abs(b[2].item() - a[2].item()) < tol * abs(a[2].item())
+    worst = max(((b[3][k].double() - a[3][k].double()).norm() / a[3][k].double().norm().clamp_min(1e-30)).item() for k in a[3])
+    assert worst < 30 * tol, worst
