@@ -31,6 +31,8 @@ if ROOT not in sys.path:
 
 import torch  # noqa: E402
 
+PREC_DESC = {"fp32": "fp32 FMA pipe", "bf16x3": "tcgen05 bf16x3 error-compensated operands, fp32 accumulate (fp32 parity, 1e-4)",
+             "bf16": "tcgen05 bf16 operands, fp32 accumulate (tolerance 5e-2 on gradients)"}
 METRIC = "train-step crystals/sec (fwd+bwd)"
 UNIT = "crystals/s"
 HIDDEN, GNN_LAYERS, T_LAYERS, T = 256, 3, 2, 201
@@ -165,7 +167,7 @@ def time_kernel(fn, iters=10):
     return a.elapsed_time(b) / iters * 1e-3
 
 
-def kernel_rooflines(B: int, pk):
+def kernel_rooflines(B: int, pk, precision: str):
     """Times the dominant kernels alone, on the stream they are launched on, at the shapes the step uses."""
     from dostransformer_b200 import _lib as L
     from dostransformer_b200 import ops
@@ -177,10 +179,13 @@ def kernel_rooflines(B: int, pk):
     w = torch.randn(N, K, device=dev)
     bias = torch.randn(N, device=dev)
     o = torch.empty(M, N, device=dev)
+    P = L.PRECISIONS[precision]
     sec = time_kernel(lambda: ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=o, bias=bias,
-                                           act=L.ACT_RELU))
+                                           act=L.ACT_RELU, prec=P))
     tf = 2.0 * M * N * K / sec / 1e12
-    out["roofline"] = {"kernel": "gemm_kernel<float,KC,KC> (FFN fc1 shape, fp32 FMA pipe)", "bound": "tensor",
+    kname = {"fp32": "gemm_kernel<float,KC,KC> (fp32 FMA pipe)", "bf16x3": "gemm_tc_kernel<3,256,KC,KC> (tcgen05, 3 MMAs per product)",
+             "bf16": "gemm_tc_kernel<1,256,KC,KC> (tcgen05)"}[precision]
+    out["roofline"] = {"kernel": kname + f", FFN fc1 shape M={M} N={N} K={K}", "bound": "tensor",
                        "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
                        "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
                        "algorithmic_flops_per_launch": 2.0 * M * N * K, "launch_ms": sec * 1e3,
@@ -236,7 +241,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         nmax = int(t.item())
     torch.manual_seed(0)
-    model = DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, dev, 0.0).to(dev).train()
+    model = DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, dev, 0.0, precision=args.precision).to(dev).train()
     model.max_num_nodes = nmax            # global padding length: the only cross-rank coupling besides the grads
     reducer = GradReducer(live_named_parameters(model)) if world > 1 else None
     weight = 1.0 / world
@@ -310,7 +315,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
         "config": {"workload": f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, random-split shape "
                                f"(BASELINE configs[1]/[2]), {B} crystals per GPU", "crystals_per_gpu": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "mean_nodes_per_batch": n_nodes,
-                   "mean_edges_per_batch": n_edges, "nmax": nmax, "precision": "fp32 FMA (fp32 parity path)",
+                   "mean_edges_per_batch": n_edges, "nmax": nmax, "precision": PREC_DESC[args.precision],
                    "l2_policy": "3 distinct batches rotated; per-step activations (>1 GB) exceed the 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
@@ -321,7 +326,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
     line["model_tflops"] = fl * args.steps / sec / 1e12
     if world == 1:
         try:
-            line.update(kernel_rooflines(B, pk))
+            line.update(kernel_rooflines(B, pk, args.precision))
         except Exception as ex:  # keep the headline even if the side measurement fails
             line["roofline"] = {"error": repr(ex)}
         if not args.no_cpu_baseline:
@@ -350,6 +355,8 @@ def main():
     ap.add_argument("--batch", type=int, default=512, help="crystals per GPU")
     ap.add_argument("--cpu-sample", type=int, default=16, help="crystals per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("DOST_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
+                    help="GEMM path: fp32 FMA pipe | tcgen05 bf16x3 (fp32 parity, default) | tcgen05 bf16")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -399,7 +399,7 @@ static int run_gemm(const dost_gemm_t* h, void* workspace, size_t workspace_byte
     kchunk = ((kchunk + 15) / 16) * 16;
     g.kchunk = kchunk;
     g.ws = (T*)workspace;
-    gz = split;
+    gz = split;   // slices past K are empty: they contribute exact zeros to the fixed-order reduction
   }
   const bool amc = h->a_mode == DOST_MC, bmc = h->b_mode == DOST_MC;
   int rc;

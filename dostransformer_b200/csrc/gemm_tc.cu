@@ -151,6 +151,60 @@ __device__ __forceinline__ uint32_t off_mnmajor(int rc, int k) {
   return static_cast<uint32_t>((rc >> 3) * 8192 + (k >> 3) * 1024 + (k & 7) * 128 + (((rc & 7) ^ (k & 7)) << 4));
 }
 
+// Fills one operand tile (ROWS x 64 bf16, SWIZZLE_128B) from fp32 global memory.  `addr(i0, i1, p, nvalid)` returns the
+// source pointer of an item (8 consecutive fp32) or nullptr, and how many of the 8 are in range.
+//   K-major  (MN_MAJOR = false): item = (row r, 16-byte chunk kc): i0 = r, i1 = kc, 8 consecutive k
+//   MN-major (MN_MAJOR = true) : item = (row chunk rc, k)        : i0 = rc, i1 = k, 8 consecutive rows
+template <bool SPLIT, int ROWS, bool MN_MAJOR, typename AddrFn>
+__device__ __forceinline__ void fill_tile(unsigned char* s_hi, unsigned char* s_lo, int pt, AddrFn addr, bool vec_ok) {
+  constexpr int kItems = ROWS * 8 / kProdThreads;   // items per thread
+  constexpr int kBatch = 4;
+  static_assert(kItems % kBatch == 0 || kItems < kBatch, "item count must be a multiple of the batch");
+  constexpr int NB = kItems < kBatch ? kItems : kBatch;
+#pragma unroll
+  for (int b0 = 0; b0 < kItems; b0 += NB) {
+    const float* p[NB];
+    int nv[NB];
+    uint32_t off[NB];
+    float4 v0[NB], v1[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int i = pt + (b0 + j) * kProdThreads;
+      int i0, i1;
+      if (!MN_MAJOR) {
+        i1 = i & 7;
+        i0 = i >> 3;
+        off[j] = off_kmajor(i0, i1);
+      } else {
+        constexpr int RC = ROWS / 8;
+        i0 = i % RC;
+        i1 = i / RC;
+        off[j] = off_mnmajor(i0, i1);
+      }
+      addr(i0, i1, p[j], nv[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const bool fast = (p[j] != nullptr) && vec_ok && nv[j] >= 8;
+      v0[j] = fast ? __ldg(reinterpret_cast<const float4*>(p[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v1[j] = fast ? __ldg(reinterpret_cast<const float4*>(p[j]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float x[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
+      const bool fast = (p[j] != nullptr) && vec_ok && nv[j] >= 8;
+      if (!fast && p[j] != nullptr) {      // ragged edge or unaligned rows: scalar loads
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[e] = (e < nv[j]) ? __ldg(p[j] + e) : 0.f;
+      }
+      uint4 hi, lo;
+      convert8<SPLIT>(x, hi, lo);
+      *reinterpret_cast<uint4*>(s_hi + off[j]) = hi;
+      if (SPLIT) *reinterpret_cast<uint4*>(s_lo + off[j]) = lo;
+    }
+  }
+}
+
 template <int NSPLIT, int BN, bool A_MC, bool B_MC>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<float> g, const Sched sch) {
   constexpr bool SPLIT = NSPLIT == 3;
@@ -212,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
         kbeg = z * g.kchunk;
         kend = min(g.K, kbeg + g.kchunk);
       }
-      const int nkt = (kend - kbeg + BK - 1) / BK;
+      const int nkt = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;   // trailing split-K slices may be empty
       for (int kt = 0; kt < nkt; ++kt) {
         const int k0 = kbeg + kt * BK;
         mbar_wait(empty0 + 8 * stage, phase ^ 1);
@@ -220,6 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
         unsigned char* sAlo = sA + A_BYTES;
         unsigned char* sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
         unsigned char* sBlo = sB + B_BYTES;
+        // Loads are issued in batches of kBatch items (2 x LDG.128 each) before any conversion so that every producer
+        // thread keeps 2*kBatch independent 16-byte loads in flight (the loop is latency-bound otherwise).
         // ---------------------------------------------------------------- A tile: 128 rows x 64 k
         if (!A_MC) {
           int s = 0;
@@ -227,83 +283,56 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
           const int kstart = (s == 0) ? 0 : g.a[s - 1].kend;
           const int klim = min(kend, g.a[s].kend);
           const bool vok = g.a[s].vec_ok != 0;
-#pragma unroll
-          for (int it = 0; it < (BM * 8) / kProdThreads; ++it) {
-            const int i = pt + it * kProdThreads;
-            const int kc = i & 7, r = i >> 3;
+          const float* abase = g.a[s].base + aoff;
+          const long long ald = g.a[s].ld;
+          const int* aidx = g.a[s].idx;
+          const int adiv = g.a[s].div;
+          fill_tile<SPLIT, BM, false>(sA, sAlo, pt, [&](int r, int kc, const float*& p, int& nvalid) {
             const int m = m0 + r, kk = k0 + kc * 8;
-            const float* p = nullptr;
+            nvalid = klim - kk;
+            p = nullptr;
             if (m < g.M && kk < klim) {
-              long long row = m / g.a[s].div;
-              if (g.a[s].idx) row = __ldg(g.a[s].idx + row);
-              p = g.a[s].base + aoff + row * g.a[s].ld + (kk - kstart);
+              long long row = m / adiv;
+              if (aidx) row = __ldg(aidx + row);
+              p = abase + row * ald + (kk - kstart);
             }
-            float x[8];
-            load8(p, klim - kk, vok, x);
-            uint4 hi, lo;
-            convert8<SPLIT>(x, hi, lo);
-            const uint32_t off = off_kmajor(r, kc);
-            *reinterpret_cast<uint4*>(sA + off) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(sAlo + off) = lo;
-          }
+          }, vok);
         } else {
           const bool vok = g.a[0].vec_ok != 0;
-#pragma unroll
-          for (int it = 0; it < (BM * 8) / kProdThreads; ++it) {
-            const int i = pt + it * kProdThreads;
-            const int rc = i & 15, k = i >> 4;      // 16 chunks of 8 rows, 64 k
+          const float* abase = g.a[0].base + aoff;
+          const long long ald = g.a[0].ld;
+          fill_tile<SPLIT, BM, true>(sA, sAlo, pt, [&](int rc, int k, const float*& p, int& nvalid) {
             const int m = m0 + rc * 8, kk = k0 + k;
-            const float* p = nullptr;
-            if (m < g.M && kk < kend) p = g.a[0].base + aoff + (long long)kk * g.a[0].ld + m;
-            float x[8];
-            load8(p, g.M - m, vok, x);
-            uint4 hi, lo;
-            convert8<SPLIT>(x, hi, lo);
-            const uint32_t off = off_mnmajor(rc, k);
-            *reinterpret_cast<uint4*>(sA + off) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(sAlo + off) = lo;
-          }
+            nvalid = g.M - m;
+            p = (m < g.M && kk < kend) ? abase + (long long)kk * ald + m : nullptr;
+          }, vok);
         }
         // ---------------------------------------------------------------- B tile: BN rows x 64 k
         if (!B_MC) {
           const bool vok = g.b.vec_ok != 0;
-#pragma unroll
-          for (int it = 0; it < (BN * 8) / kProdThreads; ++it) {
-            const int i = pt + it * kProdThreads;
-            const int kc = i & 7, r = i >> 3;
+          const float* bbase = g.b.base + boff;
+          const long long bld = g.b.ld;
+          fill_tile<SPLIT, BN, false>(sB, sBlo, pt, [&](int r, int kc, const float*& p, int& nvalid) {
             const int n = n0 + r, kk = k0 + kc * 8;
-            const float* p = nullptr;
-            if (n < g.N && kk < kend) p = g.b.base + boff + (long long)n * g.b.ld + kk;
-            float x[8];
-            load8(p, kend - kk, vok, x);
-            uint4 hi, lo;
-            convert8<SPLIT>(x, hi, lo);
-            const uint32_t off = off_kmajor(r, kc);
-            *reinterpret_cast<uint4*>(sB + off) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(sBlo + off) = lo;
-          }
+            nvalid = kend - kk;
+            p = (n < g.N && kk < kend) ? bbase + (long long)n * bld + kk : nullptr;
+          }, vok);
         } else {
           const bool vok = g.b.vec_ok != 0;
-          constexpr int RC = BN / 8;               // chunks of 8 rows
-#pragma unroll
-          for (int it = 0; it < (BN * 8) / kProdThreads; ++it) {
-            const int i = pt + it * kProdThreads;
-            const int rc = i % RC, k = i / RC;
+          const float* bbase = g.b.base + boff;
+          const long long bld = g.b.ld;
+          const int* bidx = g.b.idx;
+          const int bdiv = g.b.div;
+          fill_tile<SPLIT, BN, true>(sB, sBlo, pt, [&](int rc, int k, const float*& p, int& nvalid) {
             const int n = n0 + rc * 8, kk = k0 + k;
-            const float* p = nullptr;
+            nvalid = g.N - n;
+            p = nullptr;
             if (n < g.N && kk < kend) {
-              long long row = kk / g.b.div;
-              if (g.b.idx) row = __ldg(g.b.idx + row);
-              p = g.b.base + boff + row * g.b.ld + n;
+              long long row = kk / bdiv;
+              if (bidx) row = __ldg(bidx + row);
+              p = bbase + row * bld + n;
             }
-            float x[8];
-            load8(p, g.N - n, vok, x);
-            uint4 hi, lo;
-            convert8<SPLIT>(x, hi, lo);
-            const uint32_t off = off_mnmajor(rc, k);
-            *reinterpret_cast<uint4*>(sB + off) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(sBlo + off) = lo;
-          }
+          }, vok);
         }
         fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
         __syncwarp();
@@ -330,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
         kbeg = z * g.kchunk;
         kend = min(g.K, kbeg + g.kchunk);
       }
-      const int nkt = (kend - kbeg + BK - 1) / BK;
+      const int nkt = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;   // trailing split-K slices may be empty
       const int buf = local & 1;
       mbar_wait(acce0 + 8 * buf, acc_phase[buf] ^ 1);     // epilogue has drained this accumulator
       tc_fence_after();
@@ -401,14 +430,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
           __syncwarp();
           if (lane == 0) mbar_arrive(acce0 + 8 * buf);
         }
-        if (!row_ok || n0 + c0 >= g.N) continue;
+        // Only `row_ok` differs between lanes.  No lane may leave this iteration early: the tcgen05.ld above is a
+        // warp-collective (.sync.aligned) instruction, so the warp reconverges explicitly at the end of every chunk.
+        if (row_ok && n0 + c0 < g.N) {
         if (g.zmode == 2) {
           float* ws = g.ws + ((long long)z * g.M + m) * g.N + n0 + c0;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (n0 + c0 + j < g.N) ws[j] = empty_k ? 0.f : __uint_as_float(r[j]);
-          continue;
-        }
+        } else {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           const int n = n0 + c0 + j4 * 4;
@@ -460,6 +490,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
             }
           }
         }
+        }  // zmode
+        }  // row_ok
+        __syncwarp();
       }
     }
   }

@@ -503,3 +503,21 @@ def test_tc_model_matches_fp32_path(prec, tol):
     assert abs(b[2].item() - a[2].item()) < tol * abs(a[2].item())
     worst = max(((b[3][k].double() - a[3][k].double()).norm() / a[3][k].double().norm().clamp_min(1e-30)).item() for k in a[3])
     assert worst < 30 * tol, worst
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16x3"])
+def test_splitk_with_empty_trailing_slices(prec):
+    """K = 102912 in 148 slices rounds the slice length up so that the last slice starts past K (regression: the
+    tcgen05 kernel used to dead-lock on a negative k-tile count)."""
+    M, N, K, split = 256, 256, 102912, 148
+    dy, x = _rand(K, M, seed=1), _rand(K, N, seed=2)
+    out = torch.empty(M, N, device=DEV)
+    ops.gemm_raw(M=M, N=N, K=K, a=[(dy, None)], a_mode=L.MC, b=x, b_mode=L.MC, out=out, split_k=split, prec=L.PRECISIONS[prec])
+    assert relerr(out, dy.double().T @ x.double()) < 3e-5
+    # many tiles per CTA with a ragged last M tile, batched (attention shape): exercises accumulator double buffering
+    S, T2, H2 = 160, 201, 256
+    q, k = _rand(S, T2, H2, seed=3), _rand(S, T2, H2, seed=4)
+    sc = torch.empty(S, T2, 204, device=DEV)
+    ops.gemm_raw(M=T2, N=T2, K=H2, a=[(q.view(-1, H2), None)], a_mode=L.KC, b=k.view(-1, H2), b_mode=L.KC, out=sc, batch=S,
+                 a_bstride=T2 * H2, b_bstride=T2 * H2, c_bstride=T2 * 204, ldc=204, prec=L.PRECISIONS[prec])
+    assert relerr(sc[:, :, :T2], torch.bmm(q.double(), k.double().transpose(1, 2))) < 3e-5
