@@ -42,6 +42,27 @@ class Gemm(C.Structure):
     ]
 
 
+class PlanesC(C.Structure):
+    _fields_ = [("hi", C.c_void_p), ("lo", C.c_void_p), ("ld", C.c_longlong), ("rows", C.c_longlong), ("width", C.c_int)]
+
+
+class GemmBf16(C.Structure):
+    _fields_ = [
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
+        ("a_mode", C.c_int), ("a_nseg", C.c_int), ("a", PlanesC * 3),
+        ("b_mode", C.c_int), ("b", PlanesC),
+        ("bias", C.c_void_p),
+        ("rowbias", C.c_void_p), ("ld_rowbias", C.c_longlong), ("rowbias_div", C.c_int),
+        ("act", C.c_int), ("act_slope", C.c_float), ("prelu_slope", C.c_void_p),
+        ("out_pre", C.c_void_p), ("ld_pre", C.c_longlong),
+        ("dact_hi", C.c_void_p), ("ld_dact", C.c_longlong), ("dact_slope", C.c_float),
+        ("residual", C.c_void_p), ("ld_res", C.c_longlong),
+        ("out", C.c_void_p), ("ldc", C.c_longlong), ("accumulate", C.c_int),
+        ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_op", C.c_longlong),
+        ("split_k", C.c_int), ("precision", C.c_int),
+    ]
+
+
 _SIGNATURES = {
     "dost_abi_version": (C.c_int, []),
     "dost_last_error": (C.c_char_p, []),
@@ -53,6 +74,10 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "dost_gemm_workspace_bytes": (C.c_size_t, [C.POINTER(Gemm)]),
     "dost_gemm": (C.c_int, [C.POINTER(Gemm), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_gemm_bf16_workspace_bytes": (C.c_size_t, [C.POINTER(GemmBf16)]),
+    "dost_gemm_bf16": (C.c_int, [C.POINTER(GemmBf16), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_split_planes": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong,
+                                    C.c_void_p]),
     "dost_ln_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
     "dost_ln_bwd_workspace_bytes": (C.c_size_t, [C.c_int, C.c_longlong, C.c_int]),
@@ -104,7 +129,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 2:
+    if lib.dost_abi_version() != 3:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -1,0 +1,707 @@
+// TMA-fed tcgen05 GEMM over bf16 operand planes (sm_100a).
+//
+//   C[m,n] = epi( sum_k A(m,k) * B(n,k) ),   fp32 accumulation in TMEM.
+//
+// Operands live in HBM as bf16 "planes": hi = bf16(x) and, for the error-compensated fp32-parity mode (bf16x3),
+// lo = bf16(x - hi).  The planes are written by the kernels that produce the activations (dost_split_planes, the
+// LayerNorm kernels, this kernel's own epilogue), so the GEMM main loop is pure TMA -> shared memory -> tcgen05.mma:
+// no thread touches operand data.  (gemm_tc.cu converts fp32 operands on the fly instead and stays for gathered /
+// batched operands; its producers are bound by the L1TEX pipe at ~0.2 PFLOP/s.)
+//
+// Warp roles (320 threads, one persistent CTA per SM):
+//   warps 0-7  epilogue: warp w owns TMEM lanes 32 (w % 4) .. +31 and the column half w / 4 of the accumulator:
+//              tcgen05.ld 32x32 fp32 chunks -> XOR-swizzled shared-memory transpose -> row-contiguous (coalesced) bias /
+//              activation / act' / residual / fp32 store and optional bf16 hi/lo plane store for the next GEMM
+//   warp  8    MMA issuer (one elected lane): 1 (bf16) or 3 (bf16x3: lo*hi + hi*lo + hi*hi) tcgen05.mma per K=16 step
+//   warp  9    TMA producer (one elected lane): cp.async.bulk.tensor.2d with SWIZZLE_128B boxes, mbarrier complete_tx
+// K-major operands (reduction index contiguous) use one {64 k, ROWS} box per plane and k-tile; MN-major operands (row
+// index contiguous: the transposed operands of the weight-gradient GEMMs) use ROWS/64 boxes of {64 rows, 64 k}.  Both
+// land in the canonical UMMA SWIZZLE_128B layouts, so nothing is ever transposed in memory.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace dost {
+namespace bf {
+
+constexpr int BM = 128, BK = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (kEpiWarps + 2) * 32;  // 320
+constexpr int kMaxStages = 6;
+constexpr int kEpiBytes = kEpiWarps * 4096;     // one XOR-swizzled 32 x 32 fp32 staging tile per epilogue warp
+constexpr int kSmemBudget = 225 * 1024;         // stages + staging (+ 1 KB alignment slack <= 227 KB)
+
+struct Maps {
+  CUtensorMap a_hi[3], a_lo[3], b_hi, b_lo;
+};
+
+struct Params {
+  int M, N, K;
+  int a_nseg, a_kend[3];
+  int a_mc, b_mc;
+  int zmode, kchunk;            // 0: single, 2: split-K (raw partials to ws)
+  int m_tiles, n_tiles, total_tiles;
+  const float* bias;
+  const float* rowbias; long long ld_rowbias; int rowbias_div;
+  int act; float act_slope; const float* prelu_slope;
+  float* out_pre; long long ld_pre;
+  const __nv_bfloat16* dact_hi; long long ld_dact; float dact_slope;
+  const float* residual; long long ld_res;
+  float* out; long long ldc; int accumulate;
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_op;
+  float* ws;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (see gemm_tc.cu): K-major SBO = 1024 B between 8-row groups; MN-major
+// SBO = 1024 B between 8-k groups and LBO = 8192 B between 64-row blocks.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  uint64_t d = static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(mn_major ? (8192 >> 4) : 1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+struct TileInfo {
+  int m0, n0, kbeg, kend, nkt, z;
+};
+template <int BN>
+__device__ __forceinline__ TileInfo tile_info(const Params& p, int tile) {
+  TileInfo t;
+  const int per_z = p.m_tiles * p.n_tiles;
+  t.z = tile / per_z;
+  const int rem = tile - t.z * per_z;
+  const int mt = rem / p.n_tiles, nt = rem - mt * p.n_tiles;
+  t.m0 = mt * BM;
+  t.n0 = nt * BN;
+  t.kbeg = 0;
+  t.kend = p.K;
+  if (p.zmode == 2) {
+    t.kbeg = t.z * p.kchunk;
+    t.kend = min(p.K, t.kbeg + p.kchunk);
+  }
+  t.nkt = (t.kend > t.kbeg) ? (t.kend - t.kbeg + BK - 1) / BK : 0;
+  return t;
+}
+
+template <int NSPLIT, int BN>
+__global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_constant__ Maps maps, const Params p) {
+  constexpr bool SPLIT = NSPLIT == 3;
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+  constexpr int NSTAGE_RAW = (kSmemBudget - kEpiBytes) / STAGE_BYTES;
+  constexpr int NSTAGE = NSTAGE_RAW < kMaxStages ? NSTAGE_RAW : kMaxStages;
+  static_assert(NSTAGE >= 2, "need at least two smem stages");
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* epi_smem = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES);
+  __shared__ __align__(8) unsigned long long bars[2 * kMaxStages + 4];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
+  const uint32_t accf0 = smem_u32(&bars[2 * kMaxStages]), acce0 = smem_u32(&bars[2 * kMaxStages + 2]);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf0 + 8 * b, 1);
+      mbar_init(acce0 + 8 * b, kEpiWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kEpiWarps) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const bool a_mc = p.a_mc != 0, b_mc = p.b_mc != 0;
+
+  if (warp == kEpiWarps + 1) {
+    // ============================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileInfo t = tile_info<BN>(p, tile);
+        int seg = 0;
+        for (int kt = 0; kt < t.nkt; ++kt) {
+          const int k0 = t.kbeg + kt * BK;
+          while (seg + 1 < p.a_nseg && k0 >= p.a_kend[seg]) ++seg;
+          const int kseg = k0 - (seg == 0 ? 0 : p.a_kend[seg - 1]);   // k inside the segment's own planes
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t bar = full0 + 8 * stage;
+          mbar_expect_tx(bar, STAGE_BYTES);
+          const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
+          if (!a_mc) {
+            tma_load_2d(sA, &maps.a_hi[seg], kseg, t.m0, bar);
+            if (SPLIT) tma_load_2d(sA + A_BYTES, &maps.a_lo[seg], kseg, t.m0, bar);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BM / 64; ++b) {
+              tma_load_2d(sA + b * 8192, &maps.a_hi[0], t.m0 + 64 * b, k0, bar);
+              if (SPLIT) tma_load_2d(sA + A_BYTES + b * 8192, &maps.a_lo[0], t.m0 + 64 * b, k0, bar);
+            }
+          }
+          if (!b_mc) {
+            tma_load_2d(sB, &maps.b_hi, k0, t.n0, bar);
+            if (SPLIT) tma_load_2d(sB + B_BYTES, &maps.b_lo, k0, t.n0, bar);
+          } else {
+#pragma unroll
+            for (int b = 0; b < BN / 64; ++b) {
+              tma_load_2d(sB + b * 8192, &maps.b_hi, t.n0 + 64 * b, k0, bar);
+              if (SPLIT) tma_load_2d(sB + B_BYTES + b * 8192, &maps.b_lo, t.n0 + 64 * b, k0, bar);
+            }
+          }
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == kEpiWarps) {
+    // ============================================================== MMA issuer
+    const uint32_t idesc = make_idesc(BN, a_mc, b_mc);
+    const uint32_t a_kstep = a_mc ? (2048 >> 4) : (32 >> 4);   // descriptor start-address advance per K = 16
+    const uint32_t b_kstep = b_mc ? (2048 >> 4) : (32 >> 4);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    int local = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const TileInfo t = tile_info<BN>(p, tile);
+      const int buf = local & 1;
+      mbar_wait(acce0 + 8 * buf, acc_phase[buf] ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + buf * BN;
+      for (int kt = 0; kt < t.nkt; ++kt) {
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
+          const uint64_t dAhi = make_desc(sA, a_mc), dBhi = make_desc(sB, b_mc);
+          const uint64_t dAlo = make_desc(sA + A_BYTES, a_mc), dBlo = make_desc(sB + B_BYTES, b_mc);
+#pragma unroll
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t a_adv = static_cast<uint64_t>(ks * a_kstep), b_adv = static_cast<uint64_t>(ks * b_kstep);
+            const uint32_t first = (kt > 0 || ks > 0) ? 1u : 0u;
+            if (SPLIT) {
+              umma_f16(tmem_d, dAlo + a_adv, dBhi + b_adv, idesc, first);
+              umma_f16(tmem_d, dAhi + a_adv, dBlo + b_adv, idesc, 1u);
+              umma_f16(tmem_d, dAhi + a_adv, dBhi + b_adv, idesc, 1u);
+            } else {
+              umma_f16(tmem_d, dAhi + a_adv, dBhi + b_adv, idesc, first);
+            }
+          }
+          umma_commit(empty0 + 8 * stage);
+          if (kt == t.nkt - 1) umma_commit(accf0 + 8 * buf);
+        }
+        __syncwarp();
+        if (++stage == NSTAGE) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (t.nkt == 0 && lane == 0) umma_commit(accf0 + 8 * buf);
+      acc_phase[buf] ^= 1;
+    }
+  } else {
+    // ============================================================== epilogue (8 warps)
+    uint32_t acc_phase[2] = {0, 0};
+    int local = 0;
+    float pslope = 0.f;
+    if (p.act == DOST_ACT_PRELU) pslope = __ldg(p.prelu_slope);
+    else if (p.act == DOST_ACT_LEAKY) pslope = p.act_slope;
+    constexpr int CH = BN / 2;                            // accumulator columns handled by this warp
+    const int quad = warp & 3, half = warp >> 2;
+    const uint32_t stg = smem_u32(epi_smem) + warp * 4096;  // this warp's 32 x 32 fp32 staging tile (128-byte rows)
+    const int rsub = lane >> 3, cj = lane & 7;             // after the transpose: rows rsub + 4 i, 16-byte column chunk cj
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+      const TileInfo t = tile_info<BN>(p, tile);
+      const int buf = local & 1;
+      mbar_wait(accf0 + 8 * buf, acc_phase[buf]);
+      acc_phase[buf] ^= 1;
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + half * CH;
+      const int mbase = t.m0 + quad * 32 + rsub;           // this thread's first row after the transpose
+      const int nbase = t.n0 + half * CH + cj * 4;
+      uint32_t r[32];
+      tmem_ld32(taddr0, r);
+#pragma unroll 1
+      for (int c0 = 0; c0 < CH; c0 += 32) {
+        tmem_ld_wait();
+        // ---- stage: lane = accumulator row; 16-byte chunk j goes to column chunk j ^ (row & 7) (conflict-free)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        if (c0 + 32 < CH) {
+          tmem_ld32(taddr0 + c0 + 32, r);                  // next chunk streams in while this one is processed
+        } else {                                           // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+        }
+        __syncwarp();
+        float v[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = rsub + 4 * i;
+          const float4 q = lds128(stg + rl * 128 + ((cj ^ (rl & 7)) << 4));
+          v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
+        }
+        __syncwarp();                                      // staging tile may be overwritten by the next chunk
+        const int n = nbase + c0;
+        if (n >= p.N || t.m0 + quad * 32 >= p.M) continue;  // N % 4 == 0: a thread's 4 columns are all in or all out
+        bool mok[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) mok[i] = mbase + 4 * i < p.M;
+        if (p.zmode == 2) {
+          float* ws = p.ws + ((long long)t.z * p.M + mbase) * p.N + n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) {
+              const float4 o = (t.nkt == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+              *reinterpret_cast<float4*>(ws + (long long)(4 * i) * p.N) = o;
+            }
+          continue;
+        }
+        if (p.bias) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w; }
+        }
+        if (p.rowbias) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)((mbase + 4 * i) / p.rowbias_div) * p.ld_rowbias + n));
+              v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
+            }
+        }
+        if (p.out_pre) {
+          float* op = p.out_pre + (long long)mbase * p.ld_pre + n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) *reinterpret_cast<float4*>(op + (long long)(4 * i) * p.ld_pre) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        }
+        if (p.act != DOST_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[i][j] = (v[i][j] > 0.f) ? v[i][j] : pslope * v[i][j];
+        }
+        if (p.dact_hi) {
+          const __nv_bfloat16* dp = p.dact_hi + (long long)mbase * p.ld_dact + n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) {
+              const uint2 sgn = __ldg(reinterpret_cast<const uint2*>(dp + (long long)(4 * i) * p.ld_dact));
+              // bf16 value > 0  <=>  sign bit clear and magnitude bits non-zero
+              const uint32_t h[4] = {sgn.x & 0xFFFFu, sgn.x >> 16, sgn.y & 0xFFFFu, sgn.y >> 16};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[i][j] *= ((h[j] & 0x8000u) == 0 && (h[j] & 0x7FFFu) != 0) ? 1.f : p.dact_slope;
+            }
+        }
+        if (p.residual) {
+          const float* rp = p.residual + (long long)mbase * p.ld_res + n;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(rp + (long long)(4 * i) * p.ld_res));
+              v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
+            }
+        }
+        if (p.out) {
+          float* op = p.out + (long long)mbase * p.ldc + n;
+          if (p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (mok[i]) {
+                const float4 q = *reinterpret_cast<const float4*>(op + (long long)(4 * i) * p.ldc);
+                v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
+              }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) *reinterpret_cast<float4*>(op + (long long)(4 * i) * p.ldc) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+        }
+        if (p.out_hi) {
+          __nv_bfloat16* hp = p.out_hi + (long long)mbase * p.ld_op + n;
+          __nv_bfloat16* lp = p.out_lo ? p.out_lo + (long long)mbase * p.ld_op + n : nullptr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) {
+              uint2 hi;
+              hi.x = pack_bf16(v[i][0], v[i][1]);
+              hi.y = pack_bf16(v[i][2], v[i][3]);
+              *reinterpret_cast<uint2*>(hp + (long long)(4 * i) * p.ld_op) = hi;
+              if (lp) {
+                uint2 lo;
+                lo.x = pack_bf16(v[i][0] - __uint_as_float(hi.x << 16), v[i][1] - __uint_as_float(hi.x & 0xFFFF0000u));
+                lo.y = pack_bf16(v[i][2] - __uint_as_float(hi.y << 16), v[i][3] - __uint_as_float(hi.y & 0xFFFF0000u));
+                *reinterpret_cast<uint2*>(lp + (long long)(4 * i) * p.ld_op) = lo;
+              }
+            }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kEpiWarps) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// Fixed-order reduction of split-K partials (same contract as gemm.cu): out[m,n] (+)= sum_z ws[z][m][n].
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, long long ldc, int M, int N,
+                                     int splits, int accumulate) {
+  const long long total4 = (long long)M * N / 4;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total4; i += stride) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int z = 0; z < splits; ++z) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(ws + (long long)z * M * N) + i);
+      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    const long long e = i * 4, m = e / N, n = e % N;
+    float4* op = reinterpret_cast<float4*>(out + m * ldc + n);
+    if (accumulate) {
+      const float4 q = *op;
+      s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    *op = s;
+  }
+}
+
+// fp32 [rows, cols] (ld) -> bf16 planes [rows, ldp]: hi = bf16(x), lo = bf16(x - hi) (optional).  Columns in
+// [cols, ldp) are zero-filled so that padded planes can be used as GEMM operands directly.
+__global__ void split_planes_kernel(const float* __restrict__ x, long long ld, long long rows, int cols,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ldp, int vec_ok) {
+  const int chunks = ldp / 8;                      // 8 elements (16 bytes of bf16) per thread step
+  const long long total = rows * chunks;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long r = i / chunks;
+    const int c = static_cast<int>(i - r * chunks) * 8;
+    float v[8];
+    const float* src = x + r * ld + c;
+    if (vec_ok && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    uint4 h, l;
+    uint32_t* hp = &h.x;
+    uint32_t* lp = &l.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hp[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      lp[j] = pack_bf16(v[2 * j] - __uint_as_float(hp[j] << 16), v[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + r * ldp + c) = l;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// 2-D bf16 tensor [outer rows, inner elements contiguous], row pitch ld elements; box = {64 inner, box_outer}.
+static int make_map(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("gemm_bf16: cuTensorMapEncodeTiled is not available");
+    return DOST_ERR_UNSUPPORTED;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_bf16: cuTensorMapEncodeTiled failed (%d) base=%p inner=%lld outer=%lld ld=%lld box_outer=%d", (int)r, base,
+              inner, outer, ld, box_outer);
+    return DOST_ERR_ARG;
+  }
+  return DOST_OK;
+}
+
+template <int NSPLIT, int BN>
+static int launch(const Maps& maps, const Params& p, cudaStream_t st) {
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  constexpr int NSTAGE_RAW = (kSmemBudget - kEpiBytes) / STAGE_BYTES;
+  constexpr int NSTAGE = NSTAGE_RAW < kMaxStages ? NSTAGE_RAW : kMaxStages;
+  const int smem = NSTAGE * STAGE_BYTES + kEpiBytes + 1024;
+  auto kern = gemm_bf_kernel<NSPLIT, BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+      set_error("gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return DOST_ERR_LAUNCH;
+    }
+    configured = true;
+  }
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  kern<<<grid, kThreads, smem, st>>>(maps, p);
+  return check_launch("gemm_bf16");
+}
+
+static inline bool al16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
+
+static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  DOST_REQUIRE(h->M > 0 && h->N > 0 && h->K > 0, "gemm_bf16: bad shape M=%d N=%d K=%d", h->M, h->N, h->K);
+  DOST_REQUIRE(h->precision == DOST_PREC_BF16X3 || h->precision == DOST_PREC_BF16, "gemm_bf16: precision must be bf16x3 or bf16");
+  DOST_REQUIRE(h->N % 4 == 0, "gemm_bf16: N must be a multiple of 4 (got %d)", h->N);
+  const bool split3 = h->precision == DOST_PREC_BF16X3;
+  const bool a_mc = h->a_mode == DOST_MC, b_mc = h->b_mode == DOST_MC;
+  const int nseg = a_mc ? 1 : h->a_nseg;
+  DOST_REQUIRE(nseg >= 1 && nseg <= 3, "gemm_bf16: a_nseg must be 1..3");
+  const int bn = h->N <= 64 ? 64 : (h->N <= 128 ? 128 : 256);
+
+  Maps maps;
+  Params p;
+  p.M = h->M; p.N = h->N; p.K = h->K;
+  p.a_nseg = nseg;
+  p.a_mc = a_mc; p.b_mc = b_mc;
+  int kacc = 0;
+  for (int s = 0; s < nseg; ++s) {
+    const dost_planes_t& pl = h->a[s];
+    DOST_REQUIRE(pl.hi && (!split3 || pl.lo), "gemm_bf16: A segment %d planes missing", s);
+    DOST_REQUIRE(al16(pl.hi) && al16(pl.lo) && pl.ld % 8 == 0, "gemm_bf16: A segment %d planes must be 16-byte aligned, ld %% 8 == 0", s);
+    const int width = a_mc ? h->K : pl.width;
+    if (nseg > 1) DOST_REQUIRE(width % BK == 0, "gemm_bf16: concatenated A segments need widths %% 64 == 0 (got %d)", width);
+    kacc += width;
+    p.a_kend[s] = kacc;
+    int rc;
+    if (!a_mc) {       // [M rows, width] K-major: box {64 k, 128 rows}
+      rc = make_map(&maps.a_hi[s], pl.hi, width, pl.rows, pl.ld, BM);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.a_lo[s], pl.lo, width, pl.rows, pl.ld, BM);
+    } else {           // [K rows, M] MN-major: box {64 m, 64 k}
+      rc = make_map(&maps.a_hi[s], pl.hi, h->M, h->K, pl.ld, 64);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.a_lo[s], pl.lo, h->M, h->K, pl.ld, 64);
+    }
+    if (rc != DOST_OK) return rc;
+    if (!split3) maps.a_lo[s] = maps.a_hi[s];
+  }
+  for (int s = nseg; s < 3; ++s) {
+    maps.a_hi[s] = maps.a_hi[0];
+    maps.a_lo[s] = maps.a_lo[0];
+    p.a_kend[s] = kacc;
+  }
+  DOST_REQUIRE(kacc == h->K, "gemm_bf16: A segment widths sum to %d, K=%d", kacc, h->K);
+  {
+    const dost_planes_t& pl = h->b;
+    DOST_REQUIRE(pl.hi && (!split3 || pl.lo), "gemm_bf16: B planes missing");
+    DOST_REQUIRE(al16(pl.hi) && al16(pl.lo) && pl.ld % 8 == 0, "gemm_bf16: B planes must be 16-byte aligned, ld %% 8 == 0");
+    int rc;
+    if (!b_mc) {       // [N rows, K] K-major: box {64 k, bn rows}
+      rc = make_map(&maps.b_hi, pl.hi, h->K, h->N, pl.ld, bn);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, h->N, pl.ld, bn);
+    } else {           // [K rows, N] MN-major
+      rc = make_map(&maps.b_hi, pl.hi, h->N, h->K, pl.ld, 64);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->N, h->K, pl.ld, 64);
+    }
+    if (rc != DOST_OK) return rc;
+    if (!split3) maps.b_lo = maps.b_hi;
+  }
+  const int split = h->split_k < 1 ? 1 : h->split_k;
+  p.zmode = split > 1 ? 2 : 0;
+  p.kchunk = 0;
+  p.ws = nullptr;
+  if (split > 1) {
+    DOST_REQUIRE(!h->bias && !h->rowbias && h->act == DOST_ACT_NONE && !h->out_pre && !h->dact_hi && !h->residual && !h->out_hi,
+                 "gemm_bf16: split_k supports only plain (accumulating) fp32 stores");
+    const size_t need = sizeof(float) * (size_t)split * h->M * h->N;
+    if (!workspace || workspace_bytes < need) {
+      set_error("gemm_bf16: split_k workspace too small (%zu < %zu)", workspace_bytes, need);
+      return DOST_ERR_WORKSPACE;
+    }
+    int kchunk = (h->K + split - 1) / split;
+    p.kchunk = ((kchunk + BK - 1) / BK) * BK;     // slices end on k-tile boundaries (TMA fetches whole k-tiles)
+    p.ws = (float*)workspace;
+  }
+  p.m_tiles = (h->M + BM - 1) / BM;
+  p.n_tiles = (h->N + bn - 1) / bn;
+  const long long total = (long long)p.m_tiles * p.n_tiles * split;
+  DOST_REQUIRE(total <= 0x7fffffffLL, "gemm_bf16: too many tiles");
+  p.total_tiles = (int)total;
+  p.bias = h->bias;
+  p.rowbias = h->rowbias; p.ld_rowbias = h->ld_rowbias; p.rowbias_div = h->rowbias_div < 1 ? 1 : h->rowbias_div;
+  p.act = h->act;
+  p.act_slope = (h->act == DOST_ACT_RELU) ? 0.f : h->act_slope;
+  p.prelu_slope = h->prelu_slope;
+  DOST_REQUIRE(h->act != DOST_ACT_PRELU || h->prelu_slope, "gemm_bf16: PReLU needs a slope pointer");
+  p.out_pre = h->out_pre; p.ld_pre = h->ld_pre;
+  p.dact_hi = (const __nv_bfloat16*)h->dact_hi; p.ld_dact = h->ld_dact; p.dact_slope = h->dact_slope;
+  p.residual = h->residual; p.ld_res = h->ld_res;
+  p.out = h->out; p.ldc = h->ldc; p.accumulate = h->accumulate;
+  p.out_hi = (__nv_bfloat16*)h->out_hi; p.out_lo = (__nv_bfloat16*)h->out_lo; p.ld_op = h->ld_op;
+  DOST_REQUIRE(h->out || h->out_hi, "gemm_bf16: no output");
+  DOST_REQUIRE(!h->out || (al16(h->out) && h->ldc % 4 == 0), "gemm_bf16: out must be 16-byte aligned with ldc %% 4 == 0");
+  DOST_REQUIRE(!h->bias || al16(h->bias), "gemm_bf16: bias must be 16-byte aligned");
+  DOST_REQUIRE(!h->rowbias || (al16(h->rowbias) && h->ld_rowbias % 4 == 0), "gemm_bf16: rowbias alignment");
+  DOST_REQUIRE(!h->out_pre || (al16(h->out_pre) && h->ld_pre % 4 == 0), "gemm_bf16: out_pre alignment");
+  DOST_REQUIRE(!h->residual || (al16(h->residual) && h->ld_res % 4 == 0), "gemm_bf16: residual alignment");
+  DOST_REQUIRE(!h->dact_hi || (((uintptr_t)h->dact_hi & 7) == 0 && h->ld_dact % 4 == 0), "gemm_bf16: dact plane alignment");
+  DOST_REQUIRE(!h->out_hi || (((uintptr_t)h->out_hi & 7) == 0 && ((uintptr_t)h->out_lo & 7) == 0 && h->ld_op % 4 == 0),
+               "gemm_bf16: output plane alignment");
+
+  int rc;
+  if (split3) {
+    rc = bn == 64 ? launch<3, 64>(maps, p, st) : (bn == 128 ? launch<3, 128>(maps, p, st) : launch<3, 256>(maps, p, st));
+  } else {
+    rc = bn == 64 ? launch<1, 64>(maps, p, st) : (bn == 128 ? launch<1, 128>(maps, p, st) : launch<1, 256>(maps, p, st));
+  }
+  if (rc != DOST_OK) return rc;
+  if (split > 1) {
+    const long long total4 = (long long)h->M * h->N / 4;
+    int blocks = (int)min64((total4 + 255) / 256, (long long)kNumSMs * 8);
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_kernel<<<blocks, 256, 0, st>>>(p.ws, h->out, h->ldc, h->M, h->N, split, h->accumulate);
+    rc = check_launch("gemm_bf16 split-k reduce");
+  }
+  return rc;
+}
+
+}  // namespace bf
+}  // namespace dost
+
+extern "C" size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g) {
+  if (!g || g->split_k <= 1) return 0;
+  return sizeof(float) * (size_t)g->split_k * g->M * g->N;
+}
+
+extern "C" int dost_gemm_bf16(const dost_gemm_bf16_t* g, void* workspace, size_t workspace_bytes, dost_stream_t stream) {
+  DOST_REQUIRE(g != nullptr, "gemm_bf16: null descriptor");
+  return dost::bf::run(g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
+                                 dost_stream_t stream) {
+  DOST_REQUIRE(x && hi, "split_planes: null pointer");
+  DOST_REQUIRE(rows >= 0 && cols > 0 && ldp >= cols && ldp % 8 == 0, "split_planes: need ldp %% 8 == 0 and ldp >= cols");
+  DOST_REQUIRE(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "split_planes: planes must be 16-byte aligned");
+  if (rows == 0) return DOST_OK;
+  const int vec_ok = (((uintptr_t)x & 15) == 0 && ld % 4 == 0) ? 1 : 0;
+  const long long total = rows * (ldp / 8);
+  int blocks = (int)dost::min64((total + 255) / 256, (long long)dost::kNumSMs * 16);
+  if (blocks < 1) blocks = 1;
+  dost::bf::split_planes_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, ld, rows, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
+                                                                          (int)ldp, vec_ok);
+  return dost::check_launch("split_planes");
+}

@@ -114,96 +114,291 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// 8 fp32 -> 8 bf16 (hi) and, if SPLIT, 8 bf16 residuals (lo).
+// 4 fp32 -> 4 bf16 (hi, 8 bytes) and, if SPLIT, the 4 bf16 residuals (lo) of the error-compensated split.
 template <bool SPLIT>
-__device__ __forceinline__ void convert8(const float (&x)[8], uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
+__device__ __forceinline__ void convert4(const float4& x, uint2& hi, uint2& lo) {
+  hi.x = pack_bf16(x.x, x.y);
+  hi.y = pack_bf16(x.z, x.w);
+  if (SPLIT) {
+    lo.x = pack_bf16(x.x - __uint_as_float(hi.x << 16), x.y - __uint_as_float(hi.x & 0xFFFF0000u));
+    lo.y = pack_bf16(x.z - __uint_as_float(hi.y << 16), x.w - __uint_as_float(hi.y & 0xFFFF0000u));
+  }
+}
+
+// 4 consecutive fp32 starting at p (nullptr -> zeros).  `fast` (uniform over the CTA for one operand and k-tile) says
+// that every in-range item is 16-byte aligned and has all 4 elements in range.
+__device__ __forceinline__ float4 fetch4(const float* p, int nvalid, bool fast) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (fast) {
+    if (p != nullptr) v = __ldg(reinterpret_cast<const float4*>(p));
+  } else if (p != nullptr) {
+    if (nvalid > 0) v.x = __ldg(p);
+    if (nvalid > 1) v.y = __ldg(p + 1);
+    if (nvalid > 2) v.z = __ldg(p + 2);
+    if (nvalid > 3) v.w = __ldg(p + 3);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// Producer-side view of the CTA's flattened sequence of (output tile, k-tile) work items.
+//
+// Per k-tile every producer thread moves NAI + NBI items; an item is 4 consecutive fp32 in HBM (one LDG.128, lanes of a
+// warp contiguous: a warp-wide load covers 512 contiguous bytes = 4 full lines) = one 8-byte half of a 16-byte bf16
+// chunk of the SWIZZLE_128B operand tile in shared memory (STS.64, conflict-free per half-warp).
+//   K-major  operand (reduction index contiguous in HBM): item i -> row i / 16, k = 4 * (i % 16)
+//   MN-major operand (row index contiguous in HBM)      : item i -> k = i / (ROWS / 4), rows 4 * (i % (ROWS / 4))
+// with i = pt + 256 * j, j = 0 .. items-1.  Everything that does not change from one k-tile to the next (tile
+// origin, gathered row numbers, segment of a concatenated A operand, shared-memory offsets) is resolved once per
+// tile / segment / thread; the per-item work on the fast path is one predicate, one IMAD.WIDE, one LDG.128, the
+// conversion and two STS.64.
+template <int BN, bool A_MC, bool B_MC>
+struct Producer {
+  static constexpr int NAI = BM * BK / 4 / kProdThreads;   // 8
+  static constexpr int NBI = BN * BK / 4 / kProdThreads;   // 16 / 8 / 4
+  static constexpr int NI = NAI + NBI;
+  static constexpr int BW4 = BN / 4, BKS = kProdThreads / BW4;   // MN-major B: float4 per k-row, k-rows per item step
+  static constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+
+  const GemmDev<float>& g;
+  const Sched& sch;
+  const int pt;
+  // thread constants: element offset along the contiguous HBM axis (c) and index along the other axis (r) of item 0
+  int a_c, a_r, b_c, b_r;
+  uint32_t a_soff, b_soff;      // shared-memory byte offset of item 0 inside the operand tile
+  // position
+  int tile, kt, nkt, m0, n0, kbeg, kend, k0;
+  // A operand
+  int seg, kstart, klim;
+  int arow[A_MC ? 1 : NAI];
+  const float* abase;
+  int ald;
+  bool a_fast, a_pred;
+  const float* pa;
+  // B operand
+  const float* bbase;
+  int bld;
+  bool b_fast, b_pred, b_gather;
+  const float* pb;
+
+  __device__ __forceinline__ Producer(const GemmDev<float>& g_, const Sched& s_, int pt_) : g(g_), sch(s_), pt(pt_) {
+    if (!A_MC) {
+      a_c = (pt & 15) * 4;
+      a_r = pt >> 4;
+      a_soff = (a_r >> 3) * 1024 + (a_r & 7) * 128 + (((((pt & 15) >> 1) ^ (a_r & 7))) << 4) + (pt & 1) * 8;
+    } else {
+      a_c = pt >> 5;              // k row inside the k-tile (+ 8 j)
+      a_r = (pt & 31) * 4;        // first of the 4 consecutive rows
+      const int rc = (pt & 31) >> 1;
+      a_soff = (rc >> 3) * 8192 + a_c * 128 + (((rc & 7) ^ a_c) << 4) + (pt & 1) * 8;
+    }
+    if (!B_MC) {
+      b_c = (pt & 15) * 4;
+      b_r = pt >> 4;
+      b_soff = (b_r >> 3) * 1024 + (b_r & 7) * 128 + (((((pt & 15) >> 1) ^ (b_r & 7))) << 4) + (pt & 1) * 8;
+    } else {
+      b_c = pt / BW4;
+      b_r = (pt % BW4) * 4;
+      const int rc = (pt % BW4) >> 1;
+      b_soff = (rc >> 3) * 8192 + (b_c >> 3) * 1024 + (b_c & 7) * 128 + (((rc & 7) ^ (b_c & 7)) << 4) + (pt & 1) * 8;
+    }
+    bld = (int)g.b.ld;
+    b_gather = B_MC && (g.b.idx != nullptr || g.b.div != 1);
+  }
+
+  __device__ __forceinline__ bool valid() const { return tile < sch.total_tiles; }
+
+  // shared-memory byte offset of item j relative to item 0 (compile-time for unrolled j), applied to `off0`
+  __device__ __forceinline__ static uint32_t a_item_off(uint32_t off0, int j) { return off0 + j * (A_MC ? 1024 : 2048); }
+  __device__ __forceinline__ static uint32_t b_item_off(uint32_t off0, int j) {
+    if (!B_MC) return off0 + j * 2048;
+    if (BKS == 8) return off0 + j * 1024;
+    if (BKS == 16) return off0 + j * 2048;
+    // BKS == 4 (BN = 256): k = kw + 4 j toggles bit 2 of (k & 7) with the parity of j
+    return (off0 ^ ((j & 1) * 0x40)) + (j & 1) * 512 + (j >> 1) * 1024;
+  }
+
+  __device__ __forceinline__ void enter_segment() {     // K-major A: resolve the rows of this thread's items
+    kstart = (seg == 0) ? 0 : g.a[seg - 1].kend;
+    klim = min(kend, g.a[seg].kend);
+    abase = g.a[seg].base + (g.zmode == 1 ? (long long)(tile / (sch.m_tiles * sch.n_tiles)) * g.a_bstride : 0);
+    ald = (int)g.a[seg].ld;
+    if (!A_MC) {
+      const int adiv = g.a[seg].div;
+      const int* aidx = g.a[seg].idx;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    h[i] = pack_bf16(x[2 * i], x[2 * i + 1]);
-    if (SPLIT) {
-      const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xFFFF0000u);
-      l[i] = pack_bf16(x[2 * i] - h0, x[2 * i + 1] - h1);
+      for (int j = 0; j < NAI; ++j) {
+        const int m = m0 + a_r + 16 * j;
+        int row = -1;
+        if (m < g.M) {
+          row = (adiv == 1) ? m : m / adiv;
+          if (aidx) row = __ldg(aidx + row);
+        }
+        arow[j] = row;
+      }
     }
   }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  if (SPLIT) lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
-__device__ __forceinline__ void load8(const float* p, int nvalid, bool vec_ok, float (&x)[8]) {
-  if (p != nullptr && nvalid >= 8 && vec_ok) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = (p != nullptr && j < nvalid) ? __ldg(p + j) : 0.f;
+  __device__ __forceinline__ void enter_ktile() {
+    k0 = kbeg + kt * BK;
+    if (!A_MC) {
+      if (k0 >= klim && seg + 1 < g.a_nseg) {
+        ++seg;
+        enter_segment();
+      }
+      a_fast = g.a[seg].vec_ok != 0 && ((klim - k0) & 3) == 0;
+      a_pred = k0 + a_c < klim;
+      pa = abase + (k0 - kstart + a_c);
+    } else {
+      a_fast = g.a[0].vec_ok != 0 && (g.M & 3) == 0;
+      a_pred = m0 + a_r < g.M;
+      pa = abase + (long long)(k0 + a_c) * ald + (m0 + a_r);
+    }
+    if (!B_MC) {
+      b_fast = g.b.vec_ok != 0 && ((kend - k0) & 3) == 0;
+      b_pred = k0 + b_c < kend;
+      pb = bbase + (long long)(n0 + b_r) * bld + (k0 + b_c);
+    } else {
+      b_fast = g.b.vec_ok != 0 && (g.N & 3) == 0;
+      b_pred = n0 + b_r < g.N;
+      pb = b_gather ? bbase + (n0 + b_r) : bbase + (long long)(k0 + b_c) * bld + (n0 + b_r);
+    }
   }
-}
 
-// Byte offset of the 16-byte chunk holding elements (row r, k = 8*kc .. 8*kc+7) in a K-major SWIZZLE_128B tile.
-__device__ __forceinline__ uint32_t off_kmajor(int r, int kc) {
-  return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((kc ^ (r & 7)) << 4));
-}
-// Byte offset of the 16-byte chunk holding elements (rows 8*rc .. 8*rc+7, reduction index k) in an MN-major tile.
-__device__ __forceinline__ uint32_t off_mnmajor(int rc, int k) {
-  return static_cast<uint32_t>((rc >> 3) * 8192 + (k >> 3) * 1024 + (k & 7) * 128 + (((rc & 7) ^ (k & 7)) << 4));
-}
+  __device__ __forceinline__ void seek() {     // first tile at or after `tile` with a non-empty reduction range
+    const int tiles_per_z = sch.m_tiles * sch.n_tiles;
+    kt = 0;
+    nkt = 0;
+    while (tile < sch.total_tiles) {
+      const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
+      const int mt = rem / sch.n_tiles, nt = rem - mt * sch.n_tiles;
+      m0 = mt * BM;
+      n0 = nt * BN;
+      kbeg = 0;
+      kend = g.K;
+      if (g.zmode == 2) {
+        kbeg = z * g.kchunk;
+        kend = min(g.K, kbeg + g.kchunk);
+      }
+      nkt = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;
+      if (nkt > 0) {
+        bbase = g.b.base + (g.zmode == 1 ? (long long)z * g.b_bstride : 0);
+        seg = 0;
+        if (!A_MC)
+          while (seg + 1 < g.a_nseg && kbeg >= g.a[seg].kend) ++seg;
+        enter_segment();
+        enter_ktile();
+        return;
+      }
+      tile += gridDim.x;
+    }
+  }
 
-// Fills one operand tile (ROWS x 64 bf16, SWIZZLE_128B) from fp32 global memory.  `addr(i0, i1, p, nvalid)` returns the
-// source pointer of an item (8 consecutive fp32) or nullptr, and how many of the 8 are in range.
-//   K-major  (MN_MAJOR = false): item = (row r, 16-byte chunk kc): i0 = r, i1 = kc, 8 consecutive k
-//   MN-major (MN_MAJOR = true) : item = (row chunk rc, k)        : i0 = rc, i1 = k, 8 consecutive rows
-template <bool SPLIT, int ROWS, bool MN_MAJOR, typename AddrFn>
-__device__ __forceinline__ void fill_tile(unsigned char* s_hi, unsigned char* s_lo, int pt, AddrFn addr, bool vec_ok) {
-  constexpr int kItems = ROWS * 8 / kProdThreads;   // items per thread
-  constexpr int kBatch = 4;
-  static_assert(kItems % kBatch == 0 || kItems < kBatch, "item count must be a multiple of the batch");
-  constexpr int NB = kItems < kBatch ? kItems : kBatch;
-#pragma unroll
-  for (int b0 = 0; b0 < kItems; b0 += NB) {
-    const float* p[NB];
-    int nv[NB];
-    uint32_t off[NB];
-    float4 v0[NB], v1[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const int i = pt + (b0 + j) * kProdThreads;
-      int i0, i1;
-      if (!MN_MAJOR) {
-        i1 = i & 7;
-        i0 = i >> 3;
-        off[j] = off_kmajor(i0, i1);
+  __device__ __forceinline__ void next() {
+    if (++kt < nkt) {
+      enter_ktile();
+      return;
+    }
+    tile += gridDim.x;
+    seek();
+  }
+
+  // ---- fast path: aligned float4 items, all four elements in range whenever the item is in range
+  __device__ __forceinline__ const float* fast_ptr(int j) const {
+    if (j < NAI) {
+      if (!A_MC) return (a_pred && arow[A_MC ? 0 : j] >= 0) ? pa + (long long)arow[A_MC ? 0 : j] * ald : nullptr;
+      return (a_pred && k0 + a_c + 8 * j < kend) ? pa + (long long)(8 * j) * ald : nullptr;
+    }
+    const int jb = j - NAI;
+    if (!B_MC) return (b_pred && n0 + b_r + 16 * jb < g.N) ? pb + (long long)(16 * jb) * bld : nullptr;
+    const int kk = k0 + b_c + BKS * jb;
+    if (!(b_pred && kk < kend)) return nullptr;
+    if (!b_gather) return pb + (long long)(BKS * jb) * bld;
+    const int bdiv = g.b.div;
+    int row = (bdiv == 1) ? kk : kk / bdiv;
+    const int* bidx = g.b.idx;
+    if (bidx) row = __ldg(bidx + row);
+    return pb + (long long)row * bld;
+  }
+
+  // ---- general path: ragged edges / unaligned operands
+  __device__ __forceinline__ void slow_ptr(int j, const float*& p, int& nvalid) const {
+    p = nullptr;
+    if (j < NAI) {
+      if (!A_MC) {
+        const int kk = k0 + a_c;
+        nvalid = klim - kk;
+        if (arow[A_MC ? 0 : j] >= 0 && nvalid > 0) p = abase + (long long)arow[A_MC ? 0 : j] * ald + (kk - kstart);
       } else {
-        constexpr int RC = ROWS / 8;
-        i0 = i % RC;
-        i1 = i / RC;
-        off[j] = off_mnmajor(i0, i1);
+        const int kk = k0 + a_c + 8 * j, m = m0 + a_r;
+        nvalid = g.M - m;
+        if (kk < kend && nvalid > 0) p = abase + (long long)kk * ald + m;
       }
-      addr(i0, i1, p[j], nv[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const bool fast = (p[j] != nullptr) && vec_ok && nv[j] >= 8;
-      v0[j] = fast ? __ldg(reinterpret_cast<const float4*>(p[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
-      v1[j] = fast ? __ldg(reinterpret_cast<const float4*>(p[j]) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      float x[8] = {v0[j].x, v0[j].y, v0[j].z, v0[j].w, v1[j].x, v1[j].y, v1[j].z, v1[j].w};
-      const bool fast = (p[j] != nullptr) && vec_ok && nv[j] >= 8;
-      if (!fast && p[j] != nullptr) {      // ragged edge or unaligned rows: scalar loads
-#pragma unroll
-        for (int e = 0; e < 8; ++e) x[e] = (e < nv[j]) ? __ldg(p[j] + e) : 0.f;
+    } else {
+      const int jb = j - NAI;
+      if (!B_MC) {
+        const int n = n0 + b_r + 16 * jb, kk = k0 + b_c;
+        nvalid = kend - kk;
+        if (n < g.N && nvalid > 0) p = bbase + (long long)n * bld + kk;
+      } else {
+        const int kk = k0 + b_c + BKS * jb, n = n0 + b_r;
+        nvalid = g.N - n;
+        if (kk < kend && nvalid > 0) {
+          const int bdiv = g.b.div;
+          int row = (bdiv == 1) ? kk : kk / bdiv;
+          const int* bidx = g.b.idx;
+          if (bidx) row = __ldg(bidx + row);
+          p = bbase + (long long)row * bld + n;
+        }
       }
-      uint4 hi, lo;
-      convert8<SPLIT>(x, hi, lo);
-      *reinterpret_cast<uint4*>(s_hi + off[j]) = hi;
-      if (SPLIT) *reinterpret_cast<uint4*>(s_lo + off[j]) = lo;
     }
   }
-}
+
+  // Loads items [J0, J0 + N) of the current k-tile.  Pointers first (the row-index loads of gathered operands
+  // overlap), then the data loads back to back.
+  template <int J0, int N>
+  __device__ __forceinline__ void load(float4 (&v)[N]) const {
+    if (a_fast && b_fast) {
+      const float* p[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) p[j] = fast_ptr(J0 + j);
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        v[j] = (p[j] != nullptr) ? __ldg(reinterpret_cast<const float4*>(p[j])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float* p;
+        int nv;
+        slow_ptr(J0 + j, p, nv);
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p != nullptr) {
+          if (nv > 0) v[j].x = __ldg(p);
+          if (nv > 1) v[j].y = __ldg(p + 1);
+          if (nv > 2) v[j].z = __ldg(p + 2);
+          if (nv > 3) v[j].w = __ldg(p + 3);
+        }
+      }
+    }
+  }
+
+  template <bool SPLIT, int J0, int N>
+  __device__ __forceinline__ void store(uint32_t stage_addr, const float4 (&v)[N]) const {
+    const uint32_t sa = stage_addr, sb = stage_addr + (SPLIT ? 2 : 1) * A_BYTES;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const bool is_a = (J0 + j) < NAI;
+      const uint32_t addr = is_a ? sa + a_item_off(a_soff, J0 + j) : sb + b_item_off(b_soff, J0 + j - NAI);
+      uint2 hi, lo;
+      convert4<SPLIT>(v[j], hi, lo);
+      sts64(addr, hi);
+      if (SPLIT) sts64(addr + (is_a ? A_BYTES : B_BYTES), lo);
+    }
+  }
+};
 
 template <int NSPLIT, int BN, bool A_MC, bool B_MC>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<float> g, const Sched sch) {
@@ -250,97 +445,40 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const GemmDev<floa
 
   if (warp >= kEpiWarps + 1) {
     // ============================================================== producers
-    const int pt = threadIdx.x - (kEpiWarps + 1) * 32;  // 0..255
+    // Software-pipelined in quarters of a k-tile over two register buffers: while one quarter is converted and
+    // stored, the loads of the next quarter (possibly of the next k-tile or output tile) are already in flight, so
+    // every producer thread keeps NI/4 .. NI/2 independent LDG.128 outstanding (the loop is L2-latency bound
+    // otherwise).
+    using Prod = Producer<BN, A_MC, B_MC>;
+    constexpr int NI = Prod::NI, Q = NI / 4;
+    static_assert(NI % 4 == 0, "items per thread must split into four groups");
+    Prod pr(g, sch, threadIdx.x - (kEpiWarps + 1) * 32);
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < sch.total_tiles; tile += gridDim.x) {
-      const int z = tile / tiles_per_z, rem = tile - z * tiles_per_z;
-      const int mt = rem / sch.n_tiles, nt = rem - mt * sch.n_tiles;
-      const int m0 = mt * BM, n0 = nt * BN;
-      int kbeg = 0, kend = g.K;
-      long long aoff = 0, boff = 0;
-      if (g.zmode == 1) {
-        aoff = (long long)z * g.a_bstride;
-        boff = (long long)z * g.b_bstride;
-      } else if (g.zmode == 2) {
-        kbeg = z * g.kchunk;
-        kend = min(g.K, kbeg + g.kchunk);
-      }
-      const int nkt = (kend > kbeg) ? (kend - kbeg + BK - 1) / BK : 0;   // trailing split-K slices may be empty
-      for (int kt = 0; kt < nkt; ++kt) {
-        const int k0 = kbeg + kt * BK;
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        unsigned char* sA = smem + stage * STAGE_BYTES;
-        unsigned char* sAlo = sA + A_BYTES;
-        unsigned char* sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
-        unsigned char* sBlo = sB + B_BYTES;
-        // Loads are issued in batches of kBatch items (2 x LDG.128 each) before any conversion so that every producer
-        // thread keeps 2*kBatch independent 16-byte loads in flight (the loop is latency-bound otherwise).
-        // ---------------------------------------------------------------- A tile: 128 rows x 64 k
-        if (!A_MC) {
-          int s = 0;
-          while (s + 1 < g.a_nseg && k0 >= g.a[s].kend) ++s;
-          const int kstart = (s == 0) ? 0 : g.a[s - 1].kend;
-          const int klim = min(kend, g.a[s].kend);
-          const bool vok = g.a[s].vec_ok != 0;
-          const float* abase = g.a[s].base + aoff;
-          const long long ald = g.a[s].ld;
-          const int* aidx = g.a[s].idx;
-          const int adiv = g.a[s].div;
-          fill_tile<SPLIT, BM, false>(sA, sAlo, pt, [&](int r, int kc, const float*& p, int& nvalid) {
-            const int m = m0 + r, kk = k0 + kc * 8;
-            nvalid = klim - kk;
-            p = nullptr;
-            if (m < g.M && kk < klim) {
-              long long row = m / adiv;
-              if (aidx) row = __ldg(aidx + row);
-              p = abase + row * ald + (kk - kstart);
-            }
-          }, vok);
-        } else {
-          const bool vok = g.a[0].vec_ok != 0;
-          const float* abase = g.a[0].base + aoff;
-          const long long ald = g.a[0].ld;
-          fill_tile<SPLIT, BM, true>(sA, sAlo, pt, [&](int rc, int k, const float*& p, int& nvalid) {
-            const int m = m0 + rc * 8, kk = k0 + k;
-            nvalid = g.M - m;
-            p = (m < g.M && kk < kend) ? abase + (long long)kk * ald + m : nullptr;
-          }, vok);
-        }
-        // ---------------------------------------------------------------- B tile: BN rows x 64 k
-        if (!B_MC) {
-          const bool vok = g.b.vec_ok != 0;
-          const float* bbase = g.b.base + boff;
-          const long long bld = g.b.ld;
-          fill_tile<SPLIT, BN, false>(sB, sBlo, pt, [&](int r, int kc, const float*& p, int& nvalid) {
-            const int n = n0 + r, kk = k0 + kc * 8;
-            nvalid = kend - kk;
-            p = (n < g.N && kk < kend) ? bbase + (long long)n * bld + kk : nullptr;
-          }, vok);
-        } else {
-          const bool vok = g.b.vec_ok != 0;
-          const float* bbase = g.b.base + boff;
-          const long long bld = g.b.ld;
-          const int* bidx = g.b.idx;
-          const int bdiv = g.b.div;
-          fill_tile<SPLIT, BN, true>(sB, sBlo, pt, [&](int rc, int k, const float*& p, int& nvalid) {
-            const int n = n0 + rc * 8, kk = k0 + k;
-            nvalid = g.N - n;
-            p = nullptr;
-            if (n < g.N && kk < kend) {
-              long long row = kk / bdiv;
-              if (bidx) row = __ldg(bidx + row);
-              p = bbase + row * bld + n;
-            }
-          }, vok);
-        }
-        fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * stage);
-        if (++stage == NSTAGE) {
-          stage = 0;
-          phase ^= 1;
-        }
+    float4 b0[Q], b1[Q];
+    pr.tile = blockIdx.x;
+    pr.seek();
+    bool more = pr.valid();
+    if (more) pr.template load<0, Q>(b0);
+    while (more) {
+      pr.template load<Q, Q>(b1);
+      mbar_wait(empty0 + 8 * stage, phase ^ 1);
+      const uint32_t sbase = smem_u32(smem) + stage * STAGE_BYTES;
+      pr.template store<SPLIT, 0, Q>(sbase, b0);
+      pr.template load<2 * Q, Q>(b0);
+      pr.template store<SPLIT, Q, Q>(sbase, b1);
+      pr.template load<3 * Q, Q>(b1);
+      pr.template store<SPLIT, 2 * Q, Q>(sbase, b0);
+      pr.next();
+      more = pr.valid();
+      if (more) pr.template load<0, Q>(b0);
+      pr.template store<SPLIT, 3 * Q, Q>(sbase, b1);
+      fence_proxy_async();      // make the generic-proxy stores visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full0 + 8 * stage);
+      if (++stage == NSTAGE) {
+        stage = 0;
+        phase ^= 1;
       }
     }
   } else if (warp == kEpiWarps) {

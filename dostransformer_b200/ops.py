@@ -211,6 +211,118 @@ def gemm_raw(*, M: int, N: int, K: int, a: Sequence[Tuple[torch.Tensor, Optional
     L.check(lib.dost_gemm(C.byref(g), L.p(ws), nb, L.stream()), "gemm")
 
 
+# =====================================================================================================
+# bf16 operand planes + TMA-fed tcgen05 GEMM (dost_gemm_bf16)
+# =====================================================================================================
+@dataclass
+class Planes:
+    """A GEMM operand stored as bf16 planes: hi = bf16(x), lo = bf16(x - hi) (None in plain-bf16 mode)."""
+    hi: torch.Tensor
+    lo: Optional[torch.Tensor]
+    rows: int
+    cols: int
+
+    @property
+    def ld(self) -> int:
+        return self.hi.stride(0)
+
+    def tensors(self):
+        return (self.hi, self.lo)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def empty_planes(rows: int, cols: int, device, with_lo: bool = True) -> Planes:
+    ld = _pad8(cols)
+    hi = torch.empty(rows, ld, dtype=torch.bfloat16, device=device)
+    lo = torch.empty(rows, ld, dtype=torch.bfloat16, device=device) if with_lo else None
+    return Planes(hi, lo, rows, cols)
+
+
+def split_planes(x2d: torch.Tensor, with_lo: Optional[bool] = None) -> Planes:
+    """fp32 [rows, cols] -> bf16 planes (one pass; padded columns are zero)."""
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2
+    if x2d.stride(1) != 1:
+        x2d = x2d.contiguous()
+    if with_lo is None:
+        with_lo = _PRECISION != L.PREC_BF16
+    rows, cols = x2d.shape
+    pl = empty_planes(rows, cols, x2d.device, with_lo)
+    L.check(L.lib().dost_split_planes(L.p(x2d), _ld(x2d), rows, cols, L.p(pl.hi), L.p(pl.lo), pl.ld, L.stream()), "split_planes")
+    return pl
+
+
+_WEIGHT_PLANES = {}
+
+
+def weight_planes(w: torch.Tensor) -> Planes:
+    """Planes of a parameter, cached until the parameter is modified in place (optimizer step)."""
+    key = (w.data_ptr(), tuple(w.shape), _PRECISION != L.PREC_BF16)
+    ver = w._version
+    hit = _WEIGHT_PLANES.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    pl = split_planes(w.detach())
+    _WEIGHT_PLANES[key] = (ver, pl)
+    return pl
+
+
+def _planes_c(pl: Planes, width: int) -> L.PlanesC:
+    c = L.PlanesC()
+    c.hi = pl.hi.data_ptr()
+    c.lo = pl.lo.data_ptr() if pl.lo is not None else None
+    c.ld = pl.ld
+    c.rows = pl.rows
+    c.width = width
+    return c
+
+
+def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: Planes, b_mode: int,
+                out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                rowbias: Optional[torch.Tensor] = None, rowbias_div: int = 1, act: int = L.ACT_NONE, act_slope: float = 0.0,
+                prelu_slope: Optional[torch.Tensor] = None, out_pre: Optional[torch.Tensor] = None,
+                dact: Optional[Planes] = None, dact_slope: float = 0.0, residual: Optional[torch.Tensor] = None,
+                accumulate: bool = False, split_k: int = 1, out_planes: Optional[Planes] = None,
+                ldc: Optional[int] = None, prec: Optional[int] = None) -> None:
+    """C = epi(A B^T) on the TMA-fed tcgen05 kernel; operands are bf16 planes (see include/dost.h)."""
+    g = L.GemmBf16()
+    g.M, g.N, g.K = M, N, K
+    g.a_mode, g.a_nseg = a_mode, len(a)
+    for i, pl in enumerate(a):
+        g.a[i] = _planes_c(pl, pl.cols if a_mode == L.KC else K)
+    g.b_mode = b_mode
+    g.b = _planes_c(b, 0)
+    g.bias = bias.data_ptr() if bias is not None else None
+    if rowbias is not None:
+        g.rowbias, g.ld_rowbias, g.rowbias_div = rowbias.data_ptr(), _ld(rowbias), rowbias_div
+    g.act, g.act_slope = act, act_slope
+    g.prelu_slope = prelu_slope.data_ptr() if prelu_slope is not None else None
+    if out_pre is not None:
+        g.out_pre, g.ld_pre = out_pre.data_ptr(), _ld(out_pre)
+    if dact is not None:
+        g.dact_hi, g.ld_dact, g.dact_slope = dact.hi.data_ptr(), dact.ld, dact_slope
+    if residual is not None:
+        g.residual, g.ld_res = residual.data_ptr(), _ld(residual)
+    if out is not None:
+        g.out = out.data_ptr()
+        g.ldc = ldc if ldc is not None else _ld(out)
+    g.accumulate = 1 if accumulate else 0
+    if out_planes is not None:
+        g.out_hi = out_planes.hi.data_ptr()
+        g.out_lo = out_planes.lo.data_ptr() if out_planes.lo is not None else None
+        g.ld_op = out_planes.ld
+    g.split_k = split_k
+    g.precision = _PRECISION if prec is None else prec
+    lib = L.lib()
+    ws, nb = None, 0
+    if split_k > 1:
+        nb = lib.dost_gemm_bf16_workspace_bytes(C.byref(g))
+        ws = _ws(nb, b.hi.device)
+    L.check(lib.dost_gemm_bf16(C.byref(g), L.p(ws), nb, L.stream()), "gemm_bf16")
+
+
 def _pick_split(M_out: int, N_out: int, K_red: int, elem: int) -> int:
     tile = 128 if elem == 4 else 64
     tiles = math.ceil(M_out / tile) * math.ceil(N_out / tile)

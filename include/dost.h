@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 2
+#define DOST_ABI_VERSION 3
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -104,6 +104,49 @@ typedef struct {
 
 size_t dost_gemm_workspace_bytes(const dost_gemm_t* g);
 int dost_gemm(const dost_gemm_t* g, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * TMA-fed tcgen05 GEMM over bf16 operand planes: the tensor-core path of the Linear / MLP stacks
+ * (same reference call sites as dost_gemm: nn.Linear in DOSTransformer.py:103-105,171,182,
+ * layers/transformer.py:143-145 and their backward).  An operand is stored as two bf16 matrices,
+ * hi = bf16(x) and lo = bf16(x - hi); precision DOST_PREC_BF16X3 accumulates hi*hi + hi*lo + lo*hi in
+ * fp32 (fp32 parity), DOST_PREC_BF16 uses hi only (lo may be NULL).  Planes are written by
+ * dost_split_planes, by the LayerNorm kernels and by this GEMM's own epilogue (out_hi / out_lo).
+ *   KC: plane[r * ld + k]  (A: r = m, B: r = n)        MC: plane[k * ld + r]
+ * epilogue: v = acc + bias[n] + rowbias[(m / rowbias_div) * ld_rowbias + n]; out_pre = v; v = act(v);
+ *           v *= (dact_hi[m, n] > 0 ? 1 : dact_slope); v += residual; out (+)= v; out_hi/out_lo = split(v)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* hi;    /* bf16 plane */
+  const void* lo;    /* bf16 residual plane or NULL */
+  long long ld;      /* leading dimension in elements, multiple of 8 */
+  long long rows;    /* rows stored */
+  int width;         /* valid columns (A, KC: the k-range this segment contributes) */
+} dost_planes_t;
+
+typedef struct {
+  int M, N, K;               /* N % 4 == 0 */
+  int a_mode, a_nseg;        /* KC: up to 3 segments concatenated along k (widths % 64 == 0 when nseg > 1) */
+  dost_planes_t a[3];
+  int b_mode;
+  dost_planes_t b;
+  const float* bias;
+  const float* rowbias; long long ld_rowbias; int rowbias_div;
+  int act; float act_slope; const float* prelu_slope;
+  float* out_pre; long long ld_pre;
+  const void* dact_hi; long long ld_dact; float dact_slope;
+  const float* residual; long long ld_res;
+  float* out; long long ldc; int accumulate;      /* out may be NULL when only planes are wanted */
+  void* out_hi; void* out_lo; long long ld_op;
+  int split_k;               /* > 1: deterministic split-K (plain fp32 stores only) */
+  int precision;             /* DOST_PREC_BF16X3 or DOST_PREC_BF16 */
+} dost_gemm_bf16_t;
+
+size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g);
+int dost_gemm_bf16(const dost_gemm_bf16_t* g, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+/* fp32 [rows, cols] (ld) -> bf16 planes [rows, ldp] (ldp % 8 == 0, columns >= cols zero-filled); lo may be NULL. */
+int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
+                      dost_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Row kernels: LayerNorm (eps = 1e-5, affine) optionally followed by PReLU -- nn.LayerNorm + nn.PReLU

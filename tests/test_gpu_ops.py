@@ -521,3 +521,87 @@ def test_splitk_with_empty_trailing_slices(prec):
     ops.gemm_raw(M=T2, N=T2, K=H2, a=[(q.view(-1, H2), None)], a_mode=L.KC, b=k.view(-1, H2), b_mode=L.KC, out=sc, batch=S,
                  a_bstride=T2 * H2, b_bstride=T2 * H2, c_bstride=T2 * 204, ldc=204, prec=L.PRECISIONS[prec])
     assert relerr(sc[:, :, :T2], torch.bmm(q.double(), k.double().transpose(1, 2))) < 3e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# TMA-fed tcgen05 GEMM over bf16 planes (dost_gemm_bf16)
+# ---------------------------------------------------------------------------------------------------------------------
+def _planes_ref(x, prec):
+    """What the tensor cores see: hi (+ lo) reconstructed in fp64."""
+    hi = x.to(torch.bfloat16)
+    if prec == "bf16":
+        return hi.double()
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.double() + lo.double()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-5), ("bf16", 1e-2)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 256), (1000, 512, 768), (333, 72, 200), (4096, 1024, 256), (128, 64, 64),
+                                   (5000, 256, 1024), (77, 260, 41)])
+def test_planes_gemm_forward_shapes(prec, tol, M, N, K):
+    torch.manual_seed(M + N + K)
+    P = L.PRECISIONS[prec]
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn(N, K, device=DEV)
+    bias = torch.randn(N, device=DEV)
+    res = torch.randn(M, N, device=DEV)
+    with ops.precision(prec):
+        ap, wp = ops.split_planes(a), ops.split_planes(w)
+        out = torch.empty(M, N, device=DEV)
+        pre = torch.empty(M, N, device=DEV)
+        op = ops.empty_planes(M, N, DEV, with_lo=prec != "bf16")
+        ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=L.KC, out=out, bias=bias, act=L.ACT_LEAKY,
+                        act_slope=0.01, out_pre=pre, residual=res, out_planes=op)
+    ref_pre = a.double() @ w.double().T + bias.double()
+    ref = torch.nn.functional.leaky_relu(ref_pre, 0.01) + res.double()
+    scale = ref_pre.abs().max()
+    assert (pre.double() - ref_pre).abs().max() / scale < tol
+    assert (out.double() - ref).abs().max() / scale < tol
+    # the planes written by the epilogue reproduce `out`
+    rec = op.hi[:, :N].double() + (op.lo[:, :N].double() if op.lo is not None else 0)
+    assert (rec - out.double()).abs().max() / out.abs().max() < (1e-4 if prec == "bf16x3" else 1e-2)
+    # exactness against what the tensor cores are fed (bf16x3 drops only the lo*lo term)
+    if prec == "bf16":
+        feed = _planes_ref(a, prec) @ _planes_ref(w, prec).T + bias.double()
+        assert (pre.double() - feed).abs().max() / scale < 2e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-5), ("bf16", 1e-2)])
+def test_planes_gemm_modes_splitk_concat(prec, tol):
+    torch.manual_seed(5)
+    with ops.precision(prec):
+        # dW-style: A = dv^T (MC), B = x^T (MC), reduction over rows, split-K with a ragged last slice
+        R, No, Ki = 3001, 512, 256
+        dv = torch.randn(R, No, device=DEV)
+        x = torch.randn(R, Ki, device=DEV)
+        dvp, xp = ops.split_planes(dv), ops.split_planes(x)
+        for split in (1, 7, 48):
+            dw = torch.empty(No, Ki, device=DEV)
+            ops.gemm_planes(M=No, N=Ki, K=R, a=[dvp], a_mode=L.MC, b=xp, b_mode=L.MC, out=dw, split_k=split)
+            ref = dv.double().T @ x.double()
+            assert (dw.double() - ref).abs().max() / ref.abs().max() < tol, split
+        # accumulate into an existing gradient
+        dw2 = dw.clone()
+        ops.gemm_planes(M=No, N=Ki, K=R, a=[dvp], a_mode=L.MC, b=xp, b_mode=L.MC, out=dw2, split_k=5, accumulate=True)
+        assert (dw2.double() - 2 * ref).abs().max() / ref.abs().max() < 2 * tol
+        # dA-style: A = dv (KC), B = W (MC): dv [R, No] @ W [No, Ki]
+        w = torch.randn(No, Ki, device=DEV)
+        wp = ops.split_planes(w)
+        da = torch.empty(R, Ki, device=DEV)
+        saved = torch.randn(R, Ki, device=DEV)
+        sp = ops.split_planes(saved)
+        ops.gemm_planes(M=R, N=Ki, K=No, a=[dvp], a_mode=L.KC, b=wp, b_mode=L.MC, out=da, dact=sp, dact_slope=0.25)
+        ref = (dv.double() @ w.double()) * torch.where(sp.hi[:, :Ki].double() > 0, 1.0, 0.25)
+        assert (da.double() - ref).abs().max() / ref.abs().max() < tol
+        # concatenated A segments + per-row-group bias, output as planes only
+        a1, a2 = torch.randn(R, 128, device=DEV), torch.randn(R, 64, device=DEV)
+        w3 = torch.randn(320, 192, device=DEV)
+        rb = torch.randn((R + 9) // 10, 320, device=DEV)
+        opl = ops.empty_planes(R, 320, DEV, with_lo=prec != "bf16")
+        ops.gemm_planes(M=R, N=320, K=192, a=[ops.split_planes(a1), ops.split_planes(a2)], a_mode=L.KC, b=ops.split_planes(w3),
+                        b_mode=L.KC, rowbias=rb, rowbias_div=10, act=L.ACT_RELU, out_planes=opl)
+        ref = torch.relu(torch.cat([a1, a2], 1).double() @ w3.double().T + rb.double().repeat_interleave(10, 0)[:R])
+        rec = opl.hi[:, :320].double() + (opl.lo[:, :320].double() if opl.lo is not None else 0)
+        assert (rec - ref).abs().max() / ref.abs().max() < (1e-4 if prec == "bf16x3" else 2e-2)
