@@ -102,10 +102,18 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
     src_map = RowMap(idx=graph.row, csr=graph.by_src)
     dst_map = RowMap(idx=graph.col, csr=graph.by_dst)
     n_layers = len(processors)
+    H = x.shape[1]
+    blocked = ops.tc_active(x) and ops.planes_ok(2 * H) and H % 64 == 0 and graph.E >= 128 and \
+        (graph.by_src is not None or not torch.is_grad_enabled())
     for i, proc in enumerate(processors):
         last = i == n_layers - 1
         segs = [(x, src_map), (x, dst_map), (e, None)]
-        if last:       # the updated edge state is never read after the last layer
+        if blocked:    # split-weight edge update on the TMA-fed tensor-core kernels (ops._EdgeBlock)
+            if last:
+                e_out = ops.edge_block(x, e, proc.edge_model.edge_mlp, graph, True)
+            else:
+                e, e_out = ops.edge_block(x, e, proc.edge_model.edge_mlp, graph, False)
+        elif last:       # the updated edge state is never read after the last layer
             e_out = mlp_ln_prelu(proc.edge_model.edge_mlp, segs, graph.E)
         else:
             e, e_out = mlp_ln_prelu(proc.edge_model.edge_mlp, segs, graph.E, residual=e, want_pre=True)
@@ -116,6 +124,8 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
 
 def _ffn(layer, y2d):
     ln1 = layer.layer_norms[1]
+    if ops.tc_active(y2d) and ops.planes_ok(y2d.shape[1]) and y2d.shape[0] >= 128:
+        return ops.ffn_block(y2d, ln1.weight, ln1.bias, layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias)
     h = ops.layer_norm(y2d, ln1.weight, ln1.bias)
     h = ops.linear([(h, None)], layer.fc1.weight, layer.fc1.bias, act=L.ACT_RELU)
     return ops.linear([(h, None)], layer.fc2.weight, layer.fc2.bias, residual=y2d)

@@ -48,6 +48,23 @@ class precision:
         return False
 
 
+class precision_value:
+    """Context manager restoring a saved precision enum (used by backward passes)."""
+
+    def __init__(self, value: int):
+        self.new = value
+
+    def __enter__(self):
+        global _PRECISION
+        self.old, _PRECISION = _PRECISION, self.new
+        return self
+
+    def __exit__(self, *exc):
+        global _PRECISION
+        _PRECISION = self.old
+        return False
+
+
 def _ws(nbytes: int, device) -> Optional[torch.Tensor]:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
@@ -321,6 +338,257 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
         nb = lib.dost_gemm_bf16_workspace_bytes(C.byref(g))
         ws = _ws(nb, b.hi.device)
     L.check(lib.dost_gemm_bf16(C.byref(g), L.p(ws), nb, L.stream()), "gemm_bf16")
+
+
+def tc_active(t: torch.Tensor) -> bool:
+    """True when `t`'s Linear stacks run on the tensor cores (bf16x3 / bf16 planes) rather than the FMA pipe."""
+    return _PRECISION != L.PREC_FMA and t.dtype == torch.float32
+
+
+def _with_lo() -> bool:
+    return _PRECISION != L.PREC_BF16
+
+
+def ln_fwd_planes(x2d: torch.Tensor, gamma, beta, slope=None, *, want_y: bool = False, want_planes: bool = True,
+                  gather_add=None):
+    """LayerNorm(+PReLU) of fp32 rows, written directly as operand planes (and/or fp32).  Returns (y, planes, stats).
+
+    gather_add = (ga, ia, gb, ib): x2d[r] += ga[ia[r]] + gb[ib[r]] first, IN PLACE (x2d then holds the LayerNorm input)."""
+    M, W = x2d.shape
+    ga = ia = gb = ib = None
+    ldg = 0
+    if gather_add is not None:
+        ga, ia, gb, ib = gather_add
+        ldg = _ld(ga)
+        assert _ld(gb) == ldg
+    dev = x2d.device
+    y = torch.empty(M, W, dtype=torch.float32, device=dev) if want_y else None
+    pl = empty_planes(M, W, dev, _with_lo()) if want_planes else None
+    stats = torch.empty(M, 2, dtype=torch.float32, device=dev)
+    L.check(L.lib().dost_ln_fwd_planes(L.p(x2d), _ld(x2d), L.p(ga), L.p(ia), L.p(gb), L.p(ib), ldg, L.p(gamma), L.p(beta),
+                                       L.p(slope), L.p(y),
+                                       L.p(pl.hi) if pl else None, L.p(pl.lo) if (pl and pl.lo is not None) else None,
+                                       pl.ld if pl else 0, L.p(stats), M, W, L.stream()), "ln_fwd_planes")
+    return y, pl, stats
+
+
+def ln_bwd_planes(dy2d, x2d, stats, gamma, beta, slope=None, *, dres=None, want_dx: bool = True, want_planes: bool = False,
+                  want_xsum: bool = False):
+    """Backward of ln_fwd_planes.  Returns (dx fp32|None, dx planes|None, dgamma, dbeta, dslope|None, colsum(dx)|None)."""
+    M, W = x2d.shape
+    dev = x2d.device
+    dx = torch.empty(M, W, dtype=torch.float32, device=dev) if want_dx else None
+    pl = empty_planes(M, W, dev, _with_lo()) if want_planes else None
+    dg = torch.empty(W, dtype=torch.float32, device=dev)
+    db = torch.empty(W, dtype=torch.float32, device=dev)
+    ds = torch.empty(1, dtype=torch.float32, device=dev) if slope is not None else None
+    xs = torch.empty(W, dtype=torch.float32, device=dev) if want_xsum else None
+    lib = L.lib()
+    nb = lib.dost_ln_bwd_planes_workspace_bytes(M, W)
+    ws = _ws(nb, dev)
+    L.check(lib.dost_ln_bwd_planes(L.p(dy2d), _ld(dy2d), L.p(x2d), _ld(x2d), L.p(stats), L.p(gamma), L.p(beta), L.p(slope),
+                                   L.p(dres), _ld(dres) if dres is not None else 0, L.p(dx),
+                                   L.p(pl.hi) if pl else None, L.p(pl.lo) if (pl and pl.lo is not None) else None,
+                                   pl.ld if pl else 0, L.p(dg), L.p(db), L.p(ds), L.p(xs), M, W, L.p(ws), nb, L.stream()),
+            "ln_bwd_planes")
+    return dx, pl, dg, db, ds, xs
+
+
+def colsum_planes(pl: Planes) -> torch.Tensor:
+    out = torch.empty(pl.cols, dtype=torch.float32, device=pl.hi.device)
+    lib = L.lib()
+    nb = lib.dost_colsum_planes_workspace_bytes(pl.rows, pl.cols)
+    ws = _ws(nb, pl.hi.device)
+    L.check(lib.dost_colsum_planes(L.p(pl.hi), L.p(pl.lo), pl.ld, pl.rows, pl.cols, L.p(out), L.p(ws), nb, L.stream()),
+            "colsum_planes")
+    return out
+
+
+def _split_for(M_out: int, N_out: int, K_red: int) -> int:
+    """Split-K factor of a weight-gradient GEMM on the planes kernel (128 x 256 tiles, 148 SMs)."""
+    bn = 64 if N_out <= 64 else (128 if N_out <= 128 else 256)
+    tiles = math.ceil(M_out / 128) * math.ceil(N_out / bn)
+    want = max(1, (2 * NUM_SMS) // tiles)
+    return int(max(1, min(want, math.ceil(K_red / 512), 256)))
+
+
+def _planes_save(pl: Planes):
+    return [pl.hi, pl.lo]
+
+
+def _planes_load(hi, lo, rows, cols) -> Planes:
+    return Planes(hi, lo, rows, cols)
+
+
+class _FFNBlock(torch.autograd.Function):
+    """out = y + fc2(relu(fc1(LN(y))))  (layers/transformer.py:141-148) on the tensor cores.
+
+    The normalised input and the 4H-wide hidden activation exist only as bf16 operand planes (written by the
+    LayerNorm kernel and by fc1's epilogue); the backward fuses relu' into the epilogue of the fc2 input-gradient GEMM
+    and the residual gradient into the LayerNorm backward.
+    """
+
+    @staticmethod
+    def forward(ctx, y, ln_w, ln_b, w1, b1, w2, b2):
+        M, H = y.shape
+        F = w1.shape[0]
+        dev = y.device
+        _, h0p, stats = ln_fwd_planes(y, ln_w, ln_b)
+        w1p, w2p = weight_planes(w1), weight_planes(w2)
+        h1p = empty_planes(M, F, dev, _with_lo())
+        gemm_planes(M=M, N=F, K=H, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p)
+        out = torch.empty(M, H, dtype=torch.float32, device=dev)
+        gemm_planes(M=M, N=H, K=F, a=[h1p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=y, out=out)
+        ctx.save_for_backward(y, stats, ln_w, ln_b, w1, w2, *_planes_save(h0p), *_planes_save(h1p))
+        ctx.prec = _PRECISION
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        y, stats, ln_w, ln_b, w1, w2, h0h, h0l, h1h, h1l = ctx.saved_tensors
+        M, H = y.shape
+        F = w1.shape[0]
+        dev = y.device
+        with precision_value(ctx.prec):
+            h0p, h1p = _planes_load(h0h, h0l, M, H), _planes_load(h1h, h1l, M, F)
+            w1p, w2p = weight_planes(w1), weight_planes(w2)
+            d_out = d_out.contiguous()
+            dop = split_planes(d_out)
+            db2 = colsum(d_out)
+            dw2 = torch.empty(H, F, dtype=torch.float32, device=dev)
+            gemm_planes(M=H, N=F, K=M, a=[dop], a_mode=L.MC, b=h1p, b_mode=L.MC, out=dw2, split_k=_split_for(H, F, M))
+            # d(relu input) = (d_out W2) * relu'(h1): relu' from the sign of the saved hi plane, result as planes only
+            dv1p = empty_planes(M, F, dev, _with_lo())
+            gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p, dact_slope=0.0, out_planes=dv1p)
+            db1 = colsum_planes(dv1p)
+            dw1 = torch.empty(F, H, dtype=torch.float32, device=dev)
+            gemm_planes(M=F, N=H, K=M, a=[dv1p], a_mode=L.MC, b=h0p, b_mode=L.MC, out=dw1, split_k=_split_for(F, H, M))
+            dh0 = torch.empty(M, H, dtype=torch.float32, device=dev)
+            gemm_planes(M=M, N=H, K=F, a=[dv1p], a_mode=L.KC, b=w1p, b_mode=L.MC, out=dh0)
+            dy, _, dg, db, _, _ = ln_bwd_planes(dh0, y, stats, ln_w, ln_b, dres=d_out)
+        return dy, dg, db, dw1, db1, dw2, db2
+
+
+def ffn_block(y2d, ln_w, ln_b, w1, b1, w2, b2):
+    return _FFNBlock.apply(y2d, ln_w, ln_b, w1, b1, w2, b2)
+
+
+def cols_view(pl: Planes, a: int, b: int) -> Planes:
+    """Column range [a, b) of an operand (a, b multiples of 8): a strided view, nothing is copied."""
+    return Planes(pl.hi[:, a:b], pl.lo[:, a:b] if pl.lo is not None else None, pl.rows, b - a)
+
+
+def get_planes(t: torch.Tensor) -> Planes:
+    """Planes attached to `t` by the kernel that produced it, else one conversion pass."""
+    pl = getattr(t, "_dost_planes", None)
+    if pl is not None and pl.rows == t.shape[0] and pl.cols == t.shape[1] and (pl.lo is not None) == _with_lo():
+        return pl
+    return split_planes(t)
+
+
+class _EdgeBlock(torch.autograd.Function):
+    """Edge update of one Processor (DOSTransformer.py:139-143,171-175 and the residual of :59):
+
+        v = W2 PReLU(LN(W1 [x[row] | x[col] | e] + b1)) + b2 ;  e_new = e + v
+
+    restructured with split weights W1 = [Ws | Wd | We]: the node terms P = x [Ws; Wd]^T are computed once per node
+    ([N, 2W]) and gathered per edge inside the LayerNorm kernel, so the first GEMM over the E edges has K = H instead of
+    3H, no [E, 3H] concatenation or gather is ever materialised, and every GEMM runs on the TMA-fed planes kernel.
+    Backward: the adjoints of the two gathers are CSR segment sums (by source / by destination) of d_pre.
+    Returns (e_new, v, e_new.hi, e_new.lo) or (v,) for the last layer.
+    """
+
+    @staticmethod
+    def forward(ctx, x, e, w1, b1, ln_w, ln_b, slope, w2, b2, graph, last):
+        N, H = x.shape
+        E = e.shape[0]
+        W = w1.shape[0]
+        dev = x.device
+        xp, ep = get_planes(x), get_planes(e)
+        w1p, w2p = weight_planes(w1), weight_planes(w2)
+        w_s, w_d, w_e = cols_view(w1p, 0, H), cols_view(w1p, H, 2 * H), cols_view(w1p, 2 * H, 3 * H)
+        P = torch.empty(N, 2 * W, dtype=torch.float32, device=dev)
+        gemm_planes(M=N, N=W, K=H, a=[xp], a_mode=L.KC, b=w_s, b_mode=L.KC, out=P[:, :W])
+        gemm_planes(M=N, N=W, K=H, a=[xp], a_mode=L.KC, b=w_d, b_mode=L.KC, out=P[:, W:])
+        pre = torch.empty(E, W, dtype=torch.float32, device=dev)
+        gemm_planes(M=E, N=W, K=H, a=[ep], a_mode=L.KC, b=w_e, b_mode=L.KC, bias=b1, out=pre)
+        _, h2p, stats = ln_fwd_planes(pre, ln_w, ln_b, slope, gather_add=(P[:, :W], graph.row, P[:, W:], graph.col))
+        v = torch.empty(E, H, dtype=torch.float32, device=dev)
+        ctx.graph, ctx.last, ctx.prec = graph, last, _PRECISION
+        ctx.save_for_backward(w1, ln_w, ln_b, slope, w2, pre, stats, *_planes_save(xp), *_planes_save(ep), *_planes_save(h2p))
+        if last:
+            gemm_planes(M=E, N=H, K=W, a=[h2p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, out=v)
+            return v
+        e_new = torch.empty(E, H, dtype=torch.float32, device=dev)
+        enp = empty_planes(E, H, dev, _with_lo())
+        gemm_planes(M=E, N=H, K=W, a=[h2p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, out_pre=v, residual=e, out=e_new,
+                    out_planes=enp)
+        lo = enp.lo if enp.lo is not None else enp.hi
+        ctx.mark_non_differentiable(enp.hi, lo)
+        return e_new, v, enp.hi, lo
+
+    @staticmethod
+    def backward(ctx, *grads):
+        w1, ln_w, ln_b, slope, w2, pre, stats, xh, xl, eh, el, hh, hl = ctx.saved_tensors
+        g: CrystalGraph = ctx.graph
+        E, W = pre.shape
+        N, H = xh.shape[0], w2.shape[0]
+        dev = pre.device
+        if ctx.last:
+            d_e_new, d_v = None, grads[0]
+        else:
+            d_e_new, d_v = grads[0], grads[1]
+        with precision_value(ctx.prec):
+            xp, ep, h2p = _planes_load(xh, xl, N, H), _planes_load(eh, el, E, H), _planes_load(hh, hl, E, W)
+            w1p, w2p = weight_planes(w1), weight_planes(w2)
+            w_s, w_d, w_e = cols_view(w1p, 0, H), cols_view(w1p, H, 2 * H), cols_view(w1p, 2 * H, 3 * H)
+            # gradient wrt v: from the aggregation path and (through e_new = e + v) from the residual stream
+            if d_v is None:
+                dv = d_e_new.contiguous()
+            elif d_e_new is None:
+                dv = d_v.contiguous()
+            else:
+                dv = torch.empty(E, H, dtype=torch.float32, device=dev)
+                _axpy2(d_v.contiguous(), d_e_new.contiguous(), dv)
+            dvp = split_planes(dv)
+            db2 = colsum(dv)
+            dw2 = torch.empty(H, W, dtype=torch.float32, device=dev)
+            gemm_planes(M=H, N=W, K=E, a=[dvp], a_mode=L.MC, b=h2p, b_mode=L.MC, out=dw2, split_k=_split_for(H, W, E))
+            dh2 = torch.empty(E, W, dtype=torch.float32, device=dev)
+            gemm_planes(M=E, N=W, K=H, a=[dvp], a_mode=L.KC, b=w2p, b_mode=L.MC, out=dh2)
+            d_pre, dpp, dgam, dbet, dslope, db1 = ln_bwd_planes(dh2, pre, stats, ln_w, ln_b, slope, want_dx=True,
+                                                                want_planes=True, want_xsum=True)
+            dw1 = torch.empty(W, 3 * H, dtype=torch.float32, device=dev)
+            gemm_planes(M=W, N=H, K=E, a=[dpp], a_mode=L.MC, b=ep, b_mode=L.MC, out=dw1[:, 2 * H:], split_k=_split_for(W, H, E))
+            d_e = torch.empty(E, H, dtype=torch.float32, device=dev)
+            gemm_planes(M=E, N=H, K=W, a=[dpp], a_mode=L.KC, b=w_e, b_mode=L.MC, out=d_e, residual=d_e_new)
+            # adjoint of the two gathers: fixed-order CSR segment sums of d_pre by source and by destination node
+            dP = torch.empty(N, 2 * W, dtype=torch.float32, device=dev)
+            segment_reduce_raw(d_pre, g.by_src.rowptr, g.by_src.perm, N, out=dP[:, :W])
+            segment_reduce_raw(d_pre, g.by_dst.rowptr, g.by_dst.perm, N, out=dP[:, W:])
+            dPp = split_planes(dP)
+            dps, dpd = cols_view(dPp, 0, W), cols_view(dPp, W, 2 * W)
+            gemm_planes(M=W, N=H, K=N, a=[dps], a_mode=L.MC, b=xp, b_mode=L.MC, out=dw1[:, :H], split_k=_split_for(W, H, N))
+            gemm_planes(M=W, N=H, K=N, a=[dpd], a_mode=L.MC, b=xp, b_mode=L.MC, out=dw1[:, H:2 * H], split_k=_split_for(W, H, N))
+            dx = torch.empty(N, H, dtype=torch.float32, device=dev)
+            gemm_planes(M=N, N=H, K=W, a=[dps], a_mode=L.KC, b=w_s, b_mode=L.MC, out=dx)
+            gemm_planes(M=N, N=H, K=W, a=[dpd], a_mode=L.KC, b=w_d, b_mode=L.MC, out=dx, accumulate=True)
+        return dx, d_e, dw1, db1, dgam, dbet, dslope, dw2, db2, None, None
+
+
+def edge_block(x, e, seq, graph: CrystalGraph, last: bool):
+    """seq = nn.Sequential(Linear(3H, 2H), LayerNorm(2H), PReLU, Linear(2H, H)).  Returns (e_new, v) or v (last layer)."""
+    args = (x, e, seq[0].weight, seq[0].bias, seq[1].weight, seq[1].bias, seq[2].weight, seq[3].weight, seq[3].bias, graph, last)
+    if last:
+        return _EdgeBlock.apply(*args)
+    e_new, v, hi, lo = _EdgeBlock.apply(*args)
+    e_new._dost_planes = Planes(hi, lo if _with_lo() else None, e_new.shape[0], e_new.shape[1])
+    return e_new, v
+
+
+def planes_ok(width: int) -> bool:
+    """Row widths the vectorised LayerNorm/planes kernels support."""
+    return width in (128, 256, 512, 1024)
 
 
 def _pick_split(M_out: int, N_out: int, K_red: int, elem: int) -> int:

@@ -148,6 +148,25 @@ int dost_gemm_bf16(const dost_gemm_bf16_t* g, void* workspace, size_t workspace_
 int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
                       dost_stream_t stream);
 
+/* fp32 row kernels of the tensor-core path (W in {128, 256, 512, 1024}): LayerNorm(+PReLU) whose output is written
+ * directly as operand planes (and/or fp32), its backward (dx as fp32 and/or planes, optional residual gradient dres
+ * added to dx, column sums of dx = bias gradient of the Linear feeding the LayerNorm), and column sums over planes.
+ * Same reference call sites as dost_ln_fwd / dost_ln_bwd / dost_colsum. */
+/* optional gather-add prologue (split-weight message passing, DOSTransformer.py:139-143,174):
+ * x[r] += ga[ia[r] * ldg + :W] + gb[ib[r] * ldg + :W], written back to x before normalising. */
+int dost_ln_fwd_planes(float* x, long long ldx, const float* ga, const int32_t* ia, const float* gb, const int32_t* ib,
+                       long long ldg, const float* gamma, const float* beta, const float* prelu_slope, float* y,
+                       void* hi, void* lo, long long ldp, float* stats, long long M, int W, dost_stream_t stream);
+size_t dost_ln_bwd_planes_workspace_bytes(long long M, int W);
+int dost_ln_bwd_planes(const float* dy, long long ld_dy, const float* x, long long ldx, const float* stats,
+                       const float* gamma, const float* beta, const float* prelu_slope, const float* dres,
+                       long long ld_dres, float* dx, void* dx_hi, void* dx_lo, long long ldp, float* dgamma,
+                       float* dbeta, float* dslope, float* dxsum, long long M, int W, void* workspace,
+                       size_t workspace_bytes, dost_stream_t stream);
+size_t dost_colsum_planes_workspace_bytes(long long M, int W);
+int dost_colsum_planes(const void* hi, const void* lo, long long ld, long long M, int W, float* out, void* workspace,
+                       size_t workspace_bytes, dost_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Row kernels: LayerNorm (eps = 1e-5, affine) optionally followed by PReLU -- nn.LayerNorm + nn.PReLU
  * in edge_mlp / node_mlp_2 (DOSTransformer.py:171,182) and layers/transformer.py:132-134,142,168-170.

@@ -12,7 +12,7 @@ from dostransformer_b200.synthetic import make_edos_batch
 B = int(os.environ.get("B", "512"))
 dev = torch.device("cuda")
 torch.manual_seed(0)
-model = DOSTransformer(3, 2, 200, 41, 2, 256, dev, 0.0).to(dev).train()
+model = DOSTransformer(3, 2, 200, 41, 2, 256, dev, 0.0, precision=os.environ.get("DOST_PRECISION", "bf16x3")).to(dev).train()
 g = make_edos_batch(B, seed=2000).to(dev)
 
 

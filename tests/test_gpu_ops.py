@@ -605,3 +605,122 @@ def test_planes_gemm_modes_splitk_concat(prec, tol):
         ref = torch.relu(torch.cat([a1, a2], 1).double() @ w3.double().T + rb.double().repeat_interleave(10, 0)[:R])
         rec = opl.hi[:, :320].double() + (opl.lo[:, :320].double() if opl.lo is not None else 0)
         assert (rec - ref).abs().max() / ref.abs().max() < (1e-4 if prec == "bf16x3" else 2e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,prelu", [(256, False), (512, True), (128, True)])
+def test_ln_planes_kernels(W, prelu):
+    torch.manual_seed(W)
+    M = 777
+    x = torch.randn(M, W, device=DEV) * 2 + 0.3
+    g = torch.randn(W, device=DEV)
+    b = torch.randn(W, device=DEV)
+    slope = torch.tensor([0.25], device=DEV) if prelu else None
+    dy = torch.randn(M, W, device=DEV)
+    dres = torch.randn(M, W, device=DEV)
+    with ops.precision("bf16x3"):
+        y, pl, stats = ops.ln_fwd_planes(x, g, b, slope, want_y=True)
+        dx, dxp, dg, db, ds, xs = ops.ln_bwd_planes(dy, x, stats, g, b, slope, dres=dres, want_planes=True, want_xsum=True)
+        cs = ops.colsum_planes(pl)
+    xd = x.double().requires_grad_(True)
+    gd, bd = g.double().requires_grad_(True), b.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd, (W,), gd, bd, 1e-5)
+    sd = None
+    if prelu:
+        sd = slope.double().requires_grad_(True)
+        ref = torch.nn.functional.prelu(ref, sd)
+    ref.backward(dy.double())
+    assert (y.double() - ref).abs().max() / ref.abs().max() < 1e-5
+    rec = pl.hi.double() + pl.lo.double()
+    assert (rec - y.double()).abs().max() / y.abs().max() < 2e-5
+    assert (cs.double() - y.double().sum(0)).abs().max() / y.double().sum(0).abs().max() < 1e-4
+    dx_ref = xd.grad + dres.double()
+    assert (dx.double() - dx_ref).abs().max() / dx_ref.abs().max() < 1e-4
+    rec = dxp.hi.double() + dxp.lo.double()
+    assert (rec - dx.double()).abs().max() / dx.abs().max() < 2e-5
+    assert (dg.double() - gd.grad).abs().max() / gd.grad.abs().max() < 1e-4
+    assert (db.double() - bd.grad).abs().max() / bd.grad.abs().max() < 1e-4
+    assert (xs.double() - xd.grad.sum(0)).abs().max() / xd.grad.sum(0).abs().max().clamp_min(1e-3) < 1e-3
+    if prelu:
+        assert abs(ds.item() - sd.grad.item()) / abs(sd.grad.item()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 3e-2)])
+def test_ffn_block_matches_torch(prec, tol):
+    torch.manual_seed(3)
+    M, H = 1000, 256
+    y = torch.randn(M, H, device=DEV)
+    ln_w = (1 + 0.1 * torch.randn(H, device=DEV)).requires_grad_(True)
+    ln_b = (0.1 * torch.randn(H, device=DEV)).requires_grad_(True)
+    w1 = (torch.randn(4 * H, H, device=DEV) / 16).requires_grad_(True)
+    b1 = (0.1 * torch.randn(4 * H, device=DEV)).requires_grad_(True)
+    w2 = (torch.randn(H, 4 * H, device=DEV) / 32).requires_grad_(True)
+    b2 = (0.1 * torch.randn(H, device=DEV)).requires_grad_(True)
+    params = [ln_w, ln_b, w1, b1, w2, b2]
+    yy = y.clone().requires_grad_(True)
+    dout = torch.randn(M, H, device=DEV)
+    with ops.precision(prec):
+        out = ops.ffn_block(yy, *params)
+        out.backward(dout)
+        # the kernel's own ReLU gate decisions (a pre-activation within rounding of zero may legitimately fall on either
+        # side; the fp64 reference below uses the same gates so that the comparison measures arithmetic, not gate flips)
+        _, h0p, _ = ops.ln_fwd_planes(y, ln_w.detach(), ln_b.detach())
+        h1p = ops.empty_planes(M, 4 * H, DEV, with_lo=prec != "bf16")
+        ops.gemm_planes(M=M, N=4 * H, K=H, a=[h0p], a_mode=L.KC, b=ops.weight_planes(w1), b_mode=L.KC, bias=b1.detach(),
+                        act=L.ACT_RELU, out_planes=h1p)
+        gate = (h1p.hi[:, :4 * H] > 0).double()
+    got = [out.detach(), yy.grad] + [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    yd = y.double().requires_grad_(True)
+    pd = [p.detach().double().requires_grad_(True) for p in params]
+    h = torch.nn.functional.layer_norm(yd, (H,), pd[0], pd[1], 1e-5)
+    ref = yd + ((h @ pd[2].T + pd[3]) * gate) @ pd[4].T + pd[5]
+    ref.backward(dout.double())
+    want = [ref.detach(), yd.grad] + [p.grad for p in pd]
+    for name, a, b in zip(["out", "dy", "dln_w", "dln_b", "dw1", "db1", "dw2", "db2"], got, want):
+        err = (a.double() - b).abs().max() / b.abs().max()
+        assert err < tol, (name, err.item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-4), ("bf16", 5e-2)])
+def test_edge_block_matches_fp32_path(prec, tol):
+    """Split-weight edge update (ops._EdgeBlock) against the gather/concat formulation on the FMA pipe."""
+    from dostransformer_b200 import nn_core
+    from dostransformer_b200.synthetic import make_edos_batch
+    torch.manual_seed(11)
+    H = 128
+    g = make_edos_batch(12, seed=77, mean_atoms=9.0).to(DEV)
+    graph = ops.build_graph(g.edge_index, g.batch, g.system)
+    x0 = torch.randn(graph.N, H, device=DEV)
+    e0 = torch.randn(graph.E, H, device=DEV)
+    proc = nn_core.make_processor(H).to(DEV)
+    seq = proc.edge_model.edge_mlp
+    with torch.no_grad():
+        seq[1].weight.add_(0.1 * torch.randn_like(seq[1].weight))
+        seq[1].bias.add_(0.1 * torch.randn_like(seq[1].bias))
+    de, dv = torch.randn(graph.E, H, device=DEV), torch.randn(graph.E, H, device=DEV)
+
+    def run(blocked):
+        x, e = x0.clone().requires_grad_(True), e0.clone().requires_grad_(True)
+        for p in seq.parameters():
+            p.grad = None
+        if blocked:
+            e_new, v = ops.edge_block(x, e, seq, graph, False)
+        else:
+            src = ops.RowMap(idx=graph.row, csr=graph.by_src)
+            dst = ops.RowMap(idx=graph.col, csr=graph.by_dst)
+            e_new, v = nn_core.mlp_ln_prelu(seq, [(x, src), (x, dst), (e, None)], graph.E, residual=e, want_pre=True)
+        ((e_new * de).sum() + (v * dv).sum()).backward()
+        return [e_new.detach(), v.detach(), x.grad, e.grad] + [p.grad.clone() for p in seq.parameters()]
+
+    with ops.precision("fp32"):
+        want = run(False)
+    with ops.precision(prec):
+        got = run(True)
+    names = ["e_new", "v", "dx", "de"] + [n for n, _ in seq.named_parameters()]
+    for name, a, b in zip(names, got, want):
+        err = ((a.double() - b.double()).norm() / b.double().norm()).item()
+        assert err < tol, (name, err)
