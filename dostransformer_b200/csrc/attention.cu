@@ -10,6 +10,16 @@
 
 namespace dost {
 
+// fp32, H in {128, 256, 512}: FMA-bound kernels in attention_v2.cu
+bool xattn_v2_supported(int H);
+int xattn_v2_fwd(const float* q, long long q_ss, const float* kv, const float* phantom, const int* ptr, const int* nmax,
+                 const float* resid, long long r_ss, float* out, float* lse, int S, int B, int Tn, int H, float scale,
+                 unsigned int thresh, float inv_keep, unsigned long long seed, cudaStream_t st);
+int xattn_v2_bwd(const float* dO, const float* q, long long q_ss, const float* kv, const float* phantom, const int* ptr,
+                 const int* nmax, const float* out, const float* resid, long long r_ss, const float* lse, float* dq, float* dkv,
+                 float* Dbuf, float* part, int S, int B, int Tn, int H, float scale, unsigned int thresh, float inv_keep,
+                 unsigned long long seed, bool do_kv, cudaStream_t st);
+
 constexpr int kQPW = 4;               // queries per warp
 constexpr int kAttWarps = 8;
 constexpr int kQPB = kQPW * kAttWarps;  // queries per block
@@ -451,6 +461,9 @@ static int run_xattn_fwd(const void* q, long long q_ss, const void* kv, const vo
                          int Tn, int H, double scale, double drop_p, unsigned long long seed, cudaStream_t st) {
   const unsigned int thresh = drop_p > 0 ? drop_threshold(drop_p) : 0u;
   const float inv_keep = drop_p > 0 ? (float)(1.0 / (1.0 - drop_p)) : 1.f;
+  if (sizeof(T) == 4 && xattn_v2_supported(H))
+    return xattn_v2_fwd((const float*)q, q_ss, (const float*)kv, (const float*)phantom, ptr, nmax, (const float*)resid, r_ss,
+                        (float*)out, lse, S, B, Tn, H, (float)scale, thresh, inv_keep, seed, st);
   dim3 grid(ceil_div(Tn, kQPB), S);
   const size_t smem = sizeof(T) * (size_t)kKT * H;
 #define DOST_XF(HV)                                                                                                  \
@@ -495,6 +508,13 @@ static int run_xattn_bwd(const void* dO, const void* q, long long q_ss, const vo
   T* Dbuf = (T*)((char*)workspace + o_D);
   T* part = (T*)((char*)workspace + o_part);
   void* csws = (char*)workspace + o_cs;
+  const bool v2 = sizeof(T) == 4 && xattn_v2_supported(H);
+  if (v2) {   // dq, D and the phantom partials from the FMA-bound kernel; dkv keeps the node-block kernel below
+    int rc2 = xattn_v2_bwd((const float*)dO, (const float*)q, q_ss, (const float*)kv, (const float*)phantom, ptr, nmax,
+                           (const float*)out, (const float*)resid, r_ss, lse, (float*)dq, (float*)dkv, (float*)Dbuf, (float*)part, S,
+                           B, Tn, H, (float)scale, thresh, inv_keep, seed, false, st);
+    if (rc2 != DOST_OK) return rc2;
+  }
   const size_t smem_q = sizeof(T) * (size_t)kKT * H;
   const size_t smem_kv = sizeof(T) * (size_t)(kNT + kAttWarps) * H;
   const int kvblocks = ceil_div(N, kNT);
@@ -504,10 +524,12 @@ static int run_xattn_bwd(const void* dO, const void* q, long long q_ss, const vo
       cudaFuncSetAttribute(xattn_bwd_q_kernel<T, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);      \
     if (smem_kv > 48 * 1024)                                                                                          \
       cudaFuncSetAttribute(xattn_bwd_kv_kernel<T, HV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);    \
-    xattn_bwd_q_kernel<T, HV><<<grid, kAttWarps * 32, smem_q, st>>>(                                                  \
-        (const T*)dO, (const T*)q, q_ss, (const T*)kv, (const T*)phantom, ptr, nmax, (const T*)out, (const T*)resid,  \
-        r_ss, lse, (T*)dq, Dbuf, part, S, B, Tn, (T)scale, thresh, inv_keep, seed);                                   \
-    count_launch();                                                                                                   \
+    if (!v2) {                                                                                                        \
+      xattn_bwd_q_kernel<T, HV><<<grid, kAttWarps * 32, smem_q, st>>>(                                                \
+          (const T*)dO, (const T*)q, q_ss, (const T*)kv, (const T*)phantom, ptr, nmax, (const T*)out, (const T*)resid, \
+          r_ss, lse, (T*)dq, Dbuf, part, S, B, Tn, (T)scale, thresh, inv_keep, seed);                                 \
+      count_launch();                                                                                                 \
+    }                                                                                                                 \
     xattn_bwd_kv_kernel<T, HV><<<kvblocks, kAttWarps * 32, smem_kv, st>>>(                                            \
         (const T*)dO, (const T*)q, q_ss, (const T*)kv, ptr, node_crystal, nmax, lse, Dbuf, (T*)dkv, S, B, Tn, N,      \
         (T)scale, thresh, inv_keep, seed);                                                                            \

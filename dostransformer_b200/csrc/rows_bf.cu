@@ -221,24 +221,28 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const float* __rest
   }
 }
 
-// out_k[c] = sum_b ws[b][k * W + c], blocks visited in order (deterministic); k = 0: dgamma, 1: dbeta, 2: dxsum, 3: dslope
-__global__ void reduce_partials_kernel(const float* __restrict__ ws, int nblk, int W, float* __restrict__ o0, float* __restrict__ o1,
-                                       float* __restrict__ o2, float* __restrict__ o3) {
+// out_k[c] = sum_b ws[b][k * W + c] in a fixed order (deterministic); k = 0: dgamma, 1: dbeta, 2: dxsum, 3: dslope.
+// Block = 32 columns x 8 partial-row lanes: lane ry sums partial blocks ry, ry + 8, ... and the 8 lanes are combined
+// through shared memory in order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ ws, int nblk, int W, float* __restrict__ o0,
+                                                              float* __restrict__ o1, float* __restrict__ o2,
+                                                              float* __restrict__ o3) {
+  __shared__ float sm[8][33];
   const int ncols = 3 * W + 1;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= ncols) return;
-  float* dst = (c < W) ? o0 : (c < 2 * W ? o1 : (c < 3 * W ? o2 : o3));
-  if (!dst) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 3 < nblk; b += 4) {
-    s0 += ws[(long long)b * ncols + c];
-    s1 += ws[(long long)(b + 1) * ncols + c];
-    s2 += ws[(long long)(b + 2) * ncols + c];
-    s3 += ws[(long long)(b + 3) * ncols + c];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < ncols)
+    for (int b = ry; b < nblk; b += 8) s += ws[(long long)b * ncols + c];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < ncols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    float* dst = (c < W) ? o0 : (c < 2 * W ? o1 : (c < 3 * W ? o2 : o3));
+    if (dst) dst[c < 3 * W ? c % W : 0] = t;
   }
-  for (; b < nblk; ++b) s0 += ws[(long long)b * ncols + c];
-  dst[c < 3 * W ? c % W : 0] = (s0 + s1) + (s2 + s3);
 }
 
 // ---------------------------------------------------------------------------------------------- column sums of planes
@@ -381,7 +385,7 @@ extern "C" int dost_ln_bwd_planes(const float* dy, long long ld_dy, const float*
   int rc = check_launch("ln_bwd_planes");
   if (rc != DOST_OK) return rc;
   const int ncols = 3 * W + 1;
-  rbf::reduce_partials_kernel<<<ceil_div(ncols, 128), 128, 0, st>>>((const float*)workspace, blocks, W, dgamma, dbeta, dxsum, dslope);
+  rbf::reduce_partials_kernel<<<ceil_div(ncols, 32), 256, 0, st>>>((const float*)workspace, blocks, W, dgamma, dbeta, dxsum, dslope);
   return check_launch("ln_bwd_planes reduce");
 }
 

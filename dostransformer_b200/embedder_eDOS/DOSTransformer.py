@@ -22,7 +22,7 @@ class DOSTransformer(nn.Module):
             raise ValueError("dostransformer_b200 kernels need n_hidden in {32, 64, 128, 256, 512}")
         h = n_hidden
         self.n_energies = n_energies
-        self.precision = precision or os.environ.get("DOST_PRECISION", "fp32")   # fp32 | bf16x3 | bf16 (ops.py)
+        self.precision = precision or os.environ.get("DOST_PRECISION", "bf16x3")   # fp32 | bf16x3 | bf16 (ops.py)
         self.attn_drop = float(attn_drop)
         # creation order == RNG order of the reference (DOSTransformer.py:17-42)
         self.embeddings = nn.Embedding(n_energies, h)

@@ -8,6 +8,7 @@ in/out projections, phonon ``alpha``) are created too, never used, and never rec
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -181,11 +182,23 @@ def dos_heads(model, x_nodes, graph: ops.CrystalGraph, graph_vec, prompt_table, 
         h = cross_stack(model.transformer_source, h, x_nodes, graph, B, T, seeds)
         return ops.linear([(h.view(B * T, H), None)], model.out_layer.weight, model.out_layer.bias).view(B, T)
 
-    g_in = ops.linear([(e2d, None), (graph_vec, per_crystal)], model.fc.weight, model.fc.bias, M=B * T,
-                      act=L.ACT_LEAKY, act_slope=0.01)
-    dos_global = branch(g_in)
-    s_in = ops.linear([(e2d, None), (graph_vec, per_crystal), (prompt_table, per_system)], model.fc_prompt.weight,
-                      model.fc_prompt.bias, M=B * T, act=L.ACT_LEAKY, act_slope=0.01)
+    if ops.tc_active(e2d) and ops.planes_gemm_ok(B * T, H, H) and not os.environ.get("DOST_NO_HEADSPLIT"):
+        # split weights: the per-crystal terms (graph vector, prompt embedding) are multiplied once per crystal and enter
+        # the [B*T, H] GEMM as a row-group bias instead of being broadcast over the T energy tokens
+        wf, wp = model.fc.weight, model.fc_prompt.weight
+        rb_g = ops.linear([(graph_vec, None)], wf[:, H:], None)
+        g_in = ops.linear([(e2d, None)], wf[:, :H], model.fc.bias, act=L.ACT_LEAKY, act_slope=0.01, rowbias=rb_g, rowbias_div=T)
+        dos_global = branch(g_in)
+        rb_s = ops.linear([(graph_vec, None), (prompt_table, RowMap(idx=graph.system, csr=graph.by_system))], wp[:, H:], None,
+                          M=B)
+        s_in = ops.linear([(e2d, None)], wp[:, :H], model.fc_prompt.bias, act=L.ACT_LEAKY, act_slope=0.01, rowbias=rb_s,
+                          rowbias_div=T)
+    else:
+        g_in = ops.linear([(e2d, None), (graph_vec, per_crystal)], model.fc.weight, model.fc.bias, M=B * T,
+                          act=L.ACT_LEAKY, act_slope=0.01)
+        dos_global = branch(g_in)
+        s_in = ops.linear([(e2d, None), (graph_vec, per_crystal), (prompt_table, per_system)], model.fc_prompt.weight,
+                          model.fc_prompt.bias, M=B * T, act=L.ACT_LEAKY, act_slope=0.01)
     dos_system = branch(s_in)
     return dos_global, dos_system
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -271,18 +272,18 @@ def split_planes(x2d: torch.Tensor, with_lo: Optional[bool] = None) -> Planes:
     return pl
 
 
-_WEIGHT_PLANES = {}
-
-
 def weight_planes(w: torch.Tensor) -> Planes:
-    """Planes of a parameter, cached until the parameter is modified in place (optimizer step)."""
-    key = (w.data_ptr(), tuple(w.shape), _PRECISION != L.PREC_BF16)
-    ver = w._version
-    hit = _WEIGHT_PLANES.get(key)
+    """Planes of a parameter (or of a strided view of one), cached ON the parameter object until it is modified in
+    place (optimizer step).  Keying on the object - not on its address - keeps the cache exact across models."""
+    base = w._base if w._base is not None else w
+    cache = base.__dict__.setdefault("_dost_weight_planes", {})
+    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), _PRECISION != L.PREC_BF16)
+    ver = base._version
+    hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
     pl = split_planes(w.detach())
-    _WEIGHT_PLANES[key] = (ver, pl)
+    cache[key] = (ver, pl)
     return pl
 
 
@@ -525,6 +526,7 @@ class _EdgeBlock(torch.autograd.Function):
                     out_planes=enp)
         lo = enp.lo if enp.lo is not None else enp.hi
         ctx.mark_non_differentiable(enp.hi, lo)
+        ctx.set_materialize_grads(False)
         return e_new, v, enp.hi, lo
 
     @staticmethod
@@ -642,6 +644,7 @@ class LinearSpec:
     act: int = L.ACT_NONE
     act_slope: float = 0.0
     want_pre: bool = False           # also return the pre-activation / pre-residual value
+    rowbias_div: int = 0             # > 0: a [M / div, N] row-group bias input follows the residual (planes path only)
 
 
 class _Linear(torch.autograd.Function):
@@ -651,26 +654,38 @@ class _Linear(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, spec: LinearSpec, weight, bias, slope, residual, *tensors):
+    def forward(ctx, spec: LinearSpec, weight, bias, slope, residual, rowbias, *tensors):
         N, K = weight.shape
         M = spec.M
         dev = weight.device
-        segs = [(tensors[ti], spec.maps[si]) for si, ti in enumerate(spec.tensor_of_seg)]
         out = torch.empty(M, N, dtype=weight.dtype, device=dev)
         need_pre = spec.want_pre or spec.act == L.ACT_PRELU
         pre = torch.empty(M, N, dtype=weight.dtype, device=dev) if need_pre else None
-        gemm_raw(M=M, N=N, K=K, a=segs, a_mode=L.KC, b=weight, b_mode=L.KC, out=out, bias=bias, act=spec.act,
-                 act_slope=spec.act_slope, prelu_slope=slope, out_pre=pre, residual=residual)
+        ctx.use_planes = _linear_on_planes(spec, weight, tensors)
+        saved_in = tensors
+        if ctx.use_planes:
+            xps = [get_planes(tensors[ti]) for ti in spec.tensor_of_seg]
+            gemm_planes(M=M, N=N, K=K, a=xps, a_mode=L.KC, b=weight_planes(weight), b_mode=L.KC, out=out, bias=bias,
+                        rowbias=rowbias, rowbias_div=max(spec.rowbias_div, 1), act=spec.act, act_slope=spec.act_slope,
+                        prelu_slope=slope, out_pre=pre, residual=residual)
+            saved_in = [t for pl in xps for t in _planes_save(pl)]     # only the operand planes are needed again
+        else:
+            assert rowbias is None, "row-group bias needs the tensor-core path"
+            segs = [(tensors[ti], spec.maps[si]) for si, ti in enumerate(spec.tensor_of_seg)]
+            gemm_raw(M=M, N=N, K=K, a=segs, a_mode=L.KC, b=weight, b_mode=L.KC, out=out, bias=bias, act=spec.act,
+                     act_slope=spec.act_slope, prelu_slope=slope, out_pre=pre, residual=residual)
         ctx.spec = spec
         ctx.prec = _PRECISION
         ctx.n_tensors = len(tensors)
-        ctx.has_bias, ctx.has_res = bias is not None, residual is not None
+        ctx.in_rows = [t.shape[0] for t in tensors]
+        ctx.in_cols = [t.shape[-1] for t in tensors]
+        ctx.has_bias, ctx.has_res, ctx.has_rowbias = bias is not None, residual is not None, rowbias is not None
         saved_act = None
         if spec.act in (L.ACT_RELU, L.ACT_LEAKY):
             saved_act = out
         elif spec.act == L.ACT_PRELU:
             saved_act = pre
-        ctx.save_for_backward(weight, slope, saved_act, *tensors)
+        ctx.save_for_backward(weight, slope, saved_act, *saved_in)
         if spec.want_pre:
             return out, pre
         return out
@@ -679,6 +694,9 @@ class _Linear(torch.autograd.Function):
     def backward(ctx, d_out, d_pre=None):
         spec: LinearSpec = ctx.spec
         weight, slope, saved_act, *tensors = ctx.saved_tensors
+        if ctx.use_planes:
+            with precision_value(ctx.prec):
+                return _Linear._backward_planes(ctx, spec, weight, slope, saved_act, tensors, d_out, d_pre)
         N, K = weight.shape
         M = spec.M
         dev, dtype = weight.device, weight.dtype
@@ -729,7 +747,7 @@ class _Linear(torch.autograd.Function):
                 k0 += w
         # ---- inputs: dA = dv @ W  [M, K], then the adjoint of each row map
         d_tensors: List[Optional[torch.Tensor]] = [None] * ctx.n_tensors
-        tens_needs = needs[5:]
+        tens_needs = needs[6:]
         if any(tens_needs):
             dA = torch.empty(M, K, dtype=dtype, device=dev)
             gemm_raw(M=M, N=K, K=N, a=[(dv, None)], a_mode=L.KC, b=weight, b_mode=L.MC, out=dA, prec=ctx.prec)
@@ -741,7 +759,98 @@ class _Linear(torch.autograd.Function):
                     piece = dA[:, k0:k0 + w]
                     d_tensors[ti] = _map_adjoint(piece, spec.maps[si], t.shape[0], d_tensors[ti])
                 k0 += w
-        return (None, d_weight, d_bias, d_slope, d_res, *d_tensors)
+        return (None, d_weight, d_bias, d_slope, d_res, None, *d_tensors)
+
+    @staticmethod
+    def _dv(ctx, spec, slope, saved_act, d_out, d_pre):
+        """Gradient wrt the pre-activation value (fp32) and the PReLU slope gradient."""
+        dev, dtype = d_out.device, d_out.dtype
+        d_slope = None
+        lib = L.lib()
+        if spec.act == L.ACT_PRELU:
+            dv = torch.empty_like(d_out)
+            d_slope = torch.empty(1, dtype=dtype, device=dev)
+            nb = lib.dost_prelu_bwd_workspace_bytes(L.dt(d_out), d_out.numel())
+            ws = _ws(nb, dev)
+            L.check(lib.dost_prelu_bwd(L.dt(d_out), L.p(d_out), L.p(saved_act), L.p(slope), L.p(dv), L.p(d_slope),
+                                       d_out.numel(), L.p(ws), nb, L.stream()), "prelu_bwd")
+        elif spec.act in (L.ACT_RELU, L.ACT_LEAKY):
+            dv = torch.empty_like(d_out)
+            cslope = _const(spec.act_slope if spec.act == L.ACT_LEAKY else 0.0, dtype, dev)
+            junk = torch.empty(1, dtype=dtype, device=dev)
+            nb = lib.dost_prelu_bwd_workspace_bytes(L.dt(d_out), d_out.numel())
+            ws = _ws(nb, dev)
+            L.check(lib.dost_prelu_bwd(L.dt(d_out), L.p(d_out), L.p(saved_act), L.p(cslope), L.p(dv), L.p(junk),
+                                       d_out.numel(), L.p(ws), nb, L.stream()), "act_bwd")
+        else:
+            dv = d_out
+            if spec.want_pre and d_pre is not None:
+                dv = torch.empty_like(d_out)
+                _axpy2(d_out, d_pre.contiguous(), dv)
+        return dv, d_slope
+
+    @staticmethod
+    def _backward_planes(ctx, spec, weight, slope, saved_act, saved_planes, d_out, d_pre):
+        N, K = weight.shape
+        M = spec.M
+        dev = weight.device
+        if d_out is None:                      # only the pre-activation output was used downstream
+            d_out = torch.zeros(M, N, dtype=weight.dtype, device=dev)
+        d_out = d_out.contiguous()
+        d_res = d_out if ctx.has_res else None
+        dv, d_slope = _Linear._dv(ctx, spec, slope, saved_act, d_out, d_pre)
+        needs = ctx.needs_input_grad
+        dvp = split_planes(dv)
+        d_bias = colsum(dv) if (ctx.has_bias and needs[2]) else None
+        d_rowbias = None
+        if ctx.has_rowbias and needs[5]:
+            div = spec.rowbias_div
+            groups = (M + div - 1) // div
+            rp = torch.arange(0, (groups + 1) * div, div, dtype=torch.int32, device=dev).clamp_(max=M)
+            d_rowbias = segment_reduce_raw(dv, rp, None, groups)
+        xps = []
+        for si, ti in enumerate(spec.tensor_of_seg):
+            xps.append(_planes_load(saved_planes[2 * si], saved_planes[2 * si + 1], ctx.in_rows[ti], ctx.in_cols[ti]))
+        d_weight = None
+        if needs[1]:
+            d_weight = torch.empty(N, K, dtype=torch.float32, device=dev)
+            k0 = 0
+            for si, ti in enumerate(spec.tensor_of_seg):
+                w = ctx.in_cols[ti]
+                gemm_planes(M=N, N=w, K=M, a=[dvp], a_mode=L.MC, b=xps[si], b_mode=L.MC, out=d_weight[:, k0:k0 + w],
+                            split_k=_split_for(N, w, M))
+                k0 += w
+        d_tensors: List[Optional[torch.Tensor]] = [None] * ctx.n_tensors
+        tens_needs = needs[6:]
+        if any(tens_needs):
+            dA = torch.empty(M, K, dtype=torch.float32, device=dev)
+            gemm_planes(M=M, N=K, K=N, a=[dvp], a_mode=L.KC, b=weight_planes(weight), b_mode=L.MC, out=dA)
+            k0 = 0
+            for si, ti in enumerate(spec.tensor_of_seg):
+                w = ctx.in_cols[ti]
+                if tens_needs[ti]:
+                    d_tensors[ti] = _map_adjoint(dA[:, k0:k0 + w], None, ctx.in_rows[ti], d_tensors[ti])
+                k0 += w
+        return (None, d_weight, d_bias, d_slope, d_res, d_rowbias, *d_tensors)
+
+
+def planes_gemm_ok(M: int, N: int, K: int) -> bool:
+    """Problem sizes worth a 128 x N tensor-core tile whose operands satisfy the TMA alignment rules."""
+    return M >= 128 and N % 8 == 0 and K % 8 == 0 and M * N * K >= (1 << 22)
+
+
+def _linear_on_planes(spec: LinearSpec, weight: torch.Tensor, tensors) -> bool:
+    """Plain (un-mapped) fp32 segments of TMA-friendly widths go to the TMA-fed tensor-core kernel."""
+    if not tc_active(weight) or os.environ.get("DOST_NO_LINPLANES"):
+        return False
+    N, K = weight.shape
+    if not planes_gemm_ok(spec.M, N, K):
+        return False
+    if any(m is not None and (m.idx is not None or m.div != 1) for m in spec.maps):
+        return False
+    if len(spec.maps) > 1 and any(tensors[ti].shape[-1] % 64 != 0 for ti in spec.tensor_of_seg):
+        return False
+    return len(spec.maps) <= 3
 
 
 def _axpy2(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor) -> None:
@@ -796,8 +905,9 @@ def _map_adjoint(piece: torch.Tensor, m: Optional[RowMap], n_src_rows: int, acc:
 def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: torch.Tensor,
            bias: Optional[torch.Tensor], *, M: Optional[int] = None, act: int = L.ACT_NONE, act_slope: float = 0.0,
            prelu_slope: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-           want_pre: bool = False):
-    """Fused Linear.  ``segments`` are concatenated along the feature axis; a tensor may appear in several."""
+           want_pre: bool = False, rowbias: Optional[torch.Tensor] = None, rowbias_div: int = 0):
+    """Fused Linear.  ``segments`` are concatenated along the feature axis; a tensor may appear in several.
+    ``rowbias`` [ceil(M / rowbias_div), N] is added to row m as rowbias[m // rowbias_div] (tensor-core path only)."""
     tensors: List[torch.Tensor] = []
     tos: List[int] = []
     for t, _ in segments:
@@ -812,8 +922,8 @@ def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: to
         t0, m0 = segments[0]
         assert m0 is None or (m0.idx is None and m0.div == 1)
         M = t0.shape[0]
-    spec = LinearSpec([m for _, m in segments], tos, M, act, act_slope, want_pre)
-    return _Linear.apply(spec, weight, bias, prelu_slope, residual, *tensors)
+    spec = LinearSpec([m for _, m in segments], tos, M, act, act_slope, want_pre, rowbias_div if rowbias is not None else 0)
+    return _Linear.apply(spec, weight, bias, prelu_slope, residual, rowbias, *tensors)
 
 
 # =====================================================================================================
@@ -826,6 +936,13 @@ class _LayerNorm(torch.autograd.Function):
         if x2.stride(-1) != 1:
             x2 = x2.contiguous()
         M, W = x2.shape
+        ctx.vec = x.dtype == torch.float32 and planes_ok(W) and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0 \
+            and not os.environ.get("DOST_NO_LNVEC")
+        if ctx.vec:       # 16-byte vectorised fp32 kernels (rows_bf.cu)
+            y, _, stats = ln_fwd_planes(x2, gamma, beta, slope, want_y=True, want_planes=False)
+            ctx.save_for_backward(x2, gamma, beta, slope, stats)
+            ctx.shape = x.shape
+            return y.view(x.shape)
         y = torch.empty(M, W, dtype=x.dtype, device=x.device)
         stats = torch.empty(M, 2, dtype=x.dtype, device=x.device)
         L.check(L.lib().dost_ln_fwd(L.dt(x), L.p(x2), _ld(x2), L.p(gamma), L.p(beta), L.p(slope), L.p(y), L.p(stats), M, W,
@@ -841,6 +958,9 @@ class _LayerNorm(torch.autograd.Function):
         dy2 = dy.reshape(M, W)
         if dy2.stride(-1) != 1:
             dy2 = dy2.contiguous()
+        if ctx.vec and dy2.stride(0) % 4 == 0 and dy2.data_ptr() % 16 == 0:
+            dx, _, dg, db, ds, _ = ln_bwd_planes(dy2, x2, stats, gamma, beta, slope)
+            return dx.view(ctx.shape), dg, db, ds
         dev, dtype = x2.device, x2.dtype
         dx = torch.empty(M, W, dtype=dtype, device=dev)
         dg = torch.empty(W, dtype=dtype, device=dev)

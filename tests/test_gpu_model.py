@@ -14,6 +14,15 @@ from oracle import dost_oracle as O
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
+# GEMM paths of the fp32 model (ops.py): "fp32" = FMA pipe, "bf16x3" = tcgen05 with error-compensated bf16 operand
+# splits (the default).  Stated tolerances: outputs / loss / node embeddings <= 1e-4 relative on both; gradients per
+# tensor <= GRAD_FLOOR relative L2 (and 3 x that in max-norm) unless the reference's own fp32 noise is larger.  The
+# bf16x3 products carry ~2^-16 relative error each (the lo*lo term and the rounding of lo are dropped), which
+# backpropagation through ~30 chained GEMMs amplifies to ~1e-3 on the most cancellation-prone tensor
+# (embeddings.weight, whose fp32 reference gradient is itself only good to 4e-4 in max-norm) - hence 2e-3 / 1e-2.
+PRECS = ["fp32", "bf16x3"]
+GRAD_FLOOR = {"fp32": (1e-4, 3e-4), "bf16x3": (2e-3, 1e-2)}       # (relative L2, max-norm) per gradient tensor
+
 
 def _step(model, g, mode, beta=1.0):
     model.train()
@@ -31,7 +40,7 @@ def _rel_l2(a, b):
     return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
 
 
-def _check_grads(grads, ref32, ref64, floor=1e-4):
+def _check_grads(grads, ref32, ref64, floor=(1e-4, 3e-4)):
     """Per tensor, against the fp64 arbiter: relative L2 error < max(1e-4, 3 x the reference's own fp32-vs-fp64 L2 noise)
     and max-norm error < max(3e-4, 3 x its max-norm noise).  ReLU/PReLU gate flips make single entries of an fp32
     gradient differ at the 1e-4..1e-3 level between ANY two fp32 evaluation orders (SURVEY.md 8c calibration), which is
@@ -42,15 +51,16 @@ def _check_grads(grads, ref32, ref64, floor=1e-4):
         n_inf = relerr(ref32[k], r64) if ref32 is not None else 0.0
         n_l2 = _rel_l2(ref32[k], r64) if ref32 is not None else 0.0
         e_inf, e_l2 = relerr(grads[k], r64), _rel_l2(grads[k], r64)
-        l2_floor = 3 * floor if r64.numel() <= 4 else floor     # a lone scalar (PReLU slope) has no averaging: L2 == max-norm
-        if not (e_l2 < max(l2_floor, 3 * n_l2) and e_inf < max(3 * floor, 3 * n_inf)):
+        l2_floor = floor[1] if r64.numel() <= 4 else floor[0]     # a lone scalar (PReLU slope) has no averaging: L2 == max-norm
+        if not (e_l2 < max(l2_floor, 3 * n_l2) and e_inf < max(floor[1], 3 * n_inf)):
             bad.append((k, e_l2, n_l2, e_inf, n_inf))
     assert not bad, bad
 
 
-def test_edos_small_golden():
+@pytest.mark.parametrize("prec", PRECS)
+def test_edos_small_golden(prec):
     fx = load_golden("edos_small.pt")
-    m = DOSTransformer(*fx["ctor_args"])
+    m = DOSTransformer(*fx["ctor_args"], precision=prec)
     m.load_state_dict(fx["state_dict"])
     m.to(DEV)
     g = CrystalBatch(**fx["batch"]).to(DEV)
@@ -59,13 +69,14 @@ def test_edos_small_golden():
     assert relerr(x, fx["x64"]) < 1e-4
     assert abs(loss.item() - fx["loss64"].item()) < 1e-4 * abs(fx["loss64"].item())
     assert sorted(k for k, p in m.named_parameters() if p.grad is None) == fx["dead"]
-    _check_grads(grads, fx["grads"], fx["grads64"])
+    _check_grads(grads, fx["grads"], fx["grads64"], floor=GRAD_FLOOR[prec])
 
 
-def test_edos_h256_golden_from_seed():
+@pytest.mark.parametrize("prec", PRECS)
+def test_edos_h256_golden_from_seed(prec):
     fx = load_golden("edos_h256.pt")
     torch.manual_seed(fx["init_seed"])
-    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device(DEV), 0.0).to(DEV)
+    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device(DEV), 0.0, precision=prec).to(DEV)
     g = make_edos_batch(fx["batch_B"], seed=fx["batch_seed"]).to(DEV)
     dg, x, ds, loss, grads = _step(m, g, "edos")
     assert relerr(dg, fx["dos_global64"]) < 1e-4 and relerr(ds, fx["dos_system64"]) < 1e-4
@@ -94,7 +105,7 @@ def test_phonon_small_golden_fp64():
     assert relerr(dg, fx["dos_global"]) < 1e-5 and relerr(ds, fx["dos_system"]) < 1e-5 and relerr(x, fx["x"]) < 1e-9
     assert abs(loss.item() - fx["loss"].item()) < 1e-5 * abs(fx["loss"].item())
     assert sorted(k for k, p in m.named_parameters() if p.grad is None) == fx["dead"]
-    _check_grads(grads, None, fx["grads"], floor=1e-4)
+    _check_grads(grads, None, fx["grads"], floor=(1e-4, 3e-4))
 
 
 def test_phonon_h256_golden_from_seed():
@@ -108,10 +119,11 @@ def test_phonon_h256_golden_from_seed():
     assert abs(loss.item() - fx["loss"].item()) < 1e-5 * abs(fx["loss"].item())
 
 
-@pytest.mark.parametrize("B,H,seed", [(16, 64, 1), (3, 128, 2), (1, 32, 3)])
-def test_edos_against_oracle_fresh_batches(B, H, seed):
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,H,seed", [(16, 64, 1), (3, 128, 2), (1, 32, 3), (40, 256, 4)])
+def test_edos_against_oracle_fresh_batches(B, H, seed, prec):
     torch.manual_seed(seed)
-    m = DOSTransformer(3, 2, 200, 41, 2, H, torch.device(DEV), 0.0)
+    m = DOSTransformer(3, 2, 200, 41, 2, H, torch.device(DEV), 0.0, precision=prec)
     sd = O.state_dict_of(m)
     g = make_edos_batch(B, seed=100 + seed, mean_atoms=10.0, max_atoms=60)
     if B > 2:      # hub: pad some neighbours to the first atom of the crystal like mat2graph.py:216-241
@@ -132,12 +144,13 @@ def test_edos_against_oracle_fresh_batches(B, H, seed):
     dg, x, ds, loss, grads = _step(m, g.clone().to(DEV), "edos")
     assert relerr(dg, rdg) < 1e-4 and relerr(ds, rds) < 1e-4 and relerr(x, rx) < 1e-4
     assert abs(loss.item() - rloss.item()) < 1e-4 * abs(rloss.item())
-    _check_grads(grads, rgrads32, rgrads)
+    _check_grads(grads, rgrads32, rgrads, floor=GRAD_FLOOR[prec])
 
 
-def test_determinism_and_eval_mode():
+@pytest.mark.parametrize("prec,H", [("fp32", 64), ("bf16x3", 64), ("bf16x3", 256)])
+def test_determinism_and_eval_mode(prec, H):
     torch.manual_seed(0)
-    m = DOSTransformer(2, 2, 200, 41, 2, 64, torch.device(DEV), 0.0).to(DEV)
+    m = DOSTransformer(2, 2, 200, 41, 2, H, torch.device(DEV), 0.0, precision=prec).to(DEV)
     g = make_edos_batch(12, seed=5).to(DEV)
     a = _step(m, g, "edos")
     b = _step(m, g, "edos")
@@ -147,7 +160,7 @@ def test_determinism_and_eval_mode():
     m.eval()
     with torch.no_grad():
         dg, x, ds = m(g)
-    assert relerr(dg, a[0]) < 1e-6
+    assert relerr(dg, a[0]) < (1e-6 if prec == "fp32" else 2e-5)   # eval skips the backward-only CSRs, same arithmetic
     # B = 1 (the reference's eval loaders): no phantom keys
     g1 = make_edos_batch(1, seed=6)
     sd = O.state_dict_of(m)
@@ -173,10 +186,11 @@ def test_transformer_encoder_module_matches_oracle():
     assert relerr(enc(xs, xs, xs), ref_self) < 1e-4
 
 
-def test_full_size_properties():
+@pytest.mark.parametrize("prec", PRECS)
+def test_full_size_properties(prec):
     """BASELINE config 2/3 shape (B=512 is benchmarked; B=96 here keeps the test short): size-independent properties."""
     torch.manual_seed(0)
-    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device(DEV), 0.0).to(DEV)
+    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device(DEV), 0.0, precision=prec).to(DEV)
     g = make_edos_batch(96, seed=9)
     gd = g.clone().to(DEV)
     dg, x, ds, loss, grads = _step(m, gd, "edos")
@@ -191,7 +205,9 @@ def test_full_size_properties():
         sub = _subset(g, [3, 17, 40]).to(DEV)
         part = m(sub)[0]
         m.max_num_nodes = None
-    assert relerr(part, full[[3, 17, 40]]) < 1e-5
+    # same arithmetic per crystal on the FMA pipe; on the tensor cores the split-K slicing of nothing in the forward
+    # changes either, but the tile a row lands in does, so agreement is at the bf16x3 product error
+    assert relerr(part, full[[3, 17, 40]]) < (1e-5 if prec == "fp32" else 1e-4)
 
 
 def _subset(g, ids):
