@@ -168,34 +168,51 @@ def time_kernel(fn, iters=10):
 
 
 def kernel_rooflines(B: int, pk, precision: str):
-    """Times the dominant kernels alone, on the stream they are launched on, at the shapes the step uses."""
+    """Times the dominant kernels alone, on the stream they are launched on, at the shapes the step uses.
+
+    `roofline`: the GEMM kernel of the FFN block (65% of the model's FLOPs): the six GEMMs of one FFN layer execution
+    (fc1/fc2 forward, two input-gradient and two weight-gradient GEMMs), algorithmic FLOPs = 2*M*N*K each.
+    `roofline_hbm`: the CSR segmented reduction that replaces scatter_sum, and the LayerNorm that writes operand planes."""
     from dostransformer_b200 import _lib as L
     from dostransformer_b200 import ops
     dev = torch.device("cuda")
     out = {}
-    # FFN fc1: [B*T, 256] x [1024, 256]^T  (the FFN is ~65% of the model's FLOPs)
-    M, N, K = B * T, 4 * HIDDEN, HIDDEN
-    a = torch.randn(M, K, device=dev)
-    w = torch.randn(N, K, device=dev)
-    bias = torch.randn(N, device=dev)
-    o = torch.empty(M, N, device=dev)
+    M, Hh, F = B * T, HIDDEN, 4 * HIDDEN
     P = L.PRECISIONS[precision]
-    sec = time_kernel(lambda: ops.gemm_raw(M=M, N=N, K=K, a=[(a, None)], a_mode=L.KC, b=w, b_mode=L.KC, out=o, bias=bias,
-                                           act=L.ACT_RELU, prec=P))
-    tf = 2.0 * M * N * K / sec / 1e12
-    kname = {"fp32": "gemm_kernel<float,KC,KC> (fp32 FMA pipe)", "bf16x3": "gemm_tc_kernel<3,256,KC,KC> (tcgen05, 3 MMAs per product)",
-             "bf16": "gemm_tc_kernel<1,256,KC,KC> (tcgen05)"}[precision]
-    out["roofline"] = {"kernel": kname + f", FFN fc1 shape M={M} N={N} K={K}", "bound": "tensor",
+    shapes = [("fc1 fwd", M, F, Hh, L.KC, L.KC, 1), ("fc2 fwd", M, Hh, F, L.KC, L.KC, 1), ("fc2 dA", M, F, Hh, L.KC, L.MC, 1),
+              ("fc1 dA", M, Hh, F, L.KC, L.MC, 1), ("fc2 dW", Hh, F, M, L.MC, L.MC, 0), ("fc1 dW", F, Hh, M, L.MC, L.MC, 0)]
+    per_shape, tot_fl, tot_s = [], 0.0, 0.0
+    for name, m, n, k, am, bm, split in shapes:
+        a = torch.randn((m, k) if am == L.KC else (k, m), device=dev)
+        b = torch.randn((n, k) if bm == L.KC else (k, n), device=dev)
+        o = torch.empty(m, n, device=dev)
+        if precision == "fp32":
+            fn = lambda: ops.gemm_raw(M=m, N=n, K=k, a=[(a, None)], a_mode=am, b=b, b_mode=bm, out=o,
+                                      split_k=(ops._pick_split(m, n, k, 4) if split == 0 else 1), prec=P)
+        else:
+            with ops.precision(precision):
+                ap, bp = ops.split_planes(a), ops.split_planes(b)
+            sk = ops._split_for(m, n, k) if split == 0 else 1
+            fn = lambda: ops.gemm_planes(M=m, N=n, K=k, a=[ap], a_mode=am, b=bp, b_mode=bm, out=o, split_k=sk, prec=P)
+        sec = time_kernel(fn)
+        fl = 2.0 * m * n * k
+        per_shape.append({"gemm": name, "M": m, "N": n, "K": k, "ms": sec * 1e3, "tflops": fl / sec / 1e12})
+        tot_fl += fl
+        tot_s += sec
+        del a, b, o
+    tf = tot_fl / tot_s / 1e12
+    kname = {"fp32": "gemm_kernel<float> (fp32 FMA pipe)",
+             "bf16x3": "bf::gemm_bf_kernel<3,256> (TMA-fed tcgen05, 3 MMAs per product: tensor-pipe work = 3x algorithmic)",
+             "bf16": "bf::gemm_bf_kernel<1,256> (TMA-fed tcgen05)"}[precision]
+    out["roofline"] = {"kernel": kname + ", the six GEMMs of one FFN layer execution", "bound": "tensor",
                        "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
-                       "traffic": None, "peak_source": pk["source"] + ", bf16 burst",
-                       "algorithmic_flops_per_launch": 2.0 * M * N * K, "launch_ms": sec * 1e3,
-                       "fp32_fma_peak_tflops": 2 * 128 * 148 * 1.965e9 / 1e12}
-    del a, w, o
+                       "traffic": NCU_TRAFFIC.get(precision), "peak_source": pk["source"] + ", bf16 burst",
+                       "algorithmic_flops_per_launch": tot_fl / len(shapes), "launch_ms": tot_s / len(shapes) * 1e3,
+                       "tensor_pipe_tflops": tf * (3 if precision == "bf16x3" else 1), "per_shape": per_shape}
     # scatter_sum as a CSR segmented reduction: [E,256] -> [N,256]
     from dostransformer_b200.synthetic import make_edos_batch
     g = make_edos_batch(B, seed=2000)
     gr = ops.build_graph(g.edge_index.to(dev), g.batch.to(dev), g.system.to(dev))
-    src = torch.randn(gr.E, HIDDEN, device=dev)
     dst = torch.empty(gr.N, HIDDEN, device=dev)
     big = [torch.randn(gr.E, HIDDEN, device=dev) for _ in range(max(1, int(300e6 // (gr.E * HIDDEN * 4))))]
     it = {"i": 0}
@@ -212,7 +229,29 @@ def kernel_rooflines(B: int, pk, precision: str):
                            "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
                            "algorithmic_bytes_per_launch": nbytes, "launch_ms": sec * 1e3, "E": gr.E, "N": gr.N,
                            "note": "inputs rotated over >300 MB so they do not sit in L2"}
+    del big
+    # LayerNorm of the [B*T, 256] token stream writing bf16 hi/lo operand planes: reads 4 B, writes 4 B per element
+    xs = [torch.randn(M, HIDDEN, device=dev) for _ in range(3)]
+    gam, bet = torch.ones(HIDDEN, device=dev), torch.zeros(HIDDEN, device=dev)
+    it2 = {"i": 0}
+
+    def ln():
+        it2["i"] += 1
+        with ops.precision("bf16x3"):
+            ops.ln_fwd_planes(xs[it2["i"] % 3], gam, bet)
+
+    sec = time_kernel(ln, iters=12)
+    nbytes = 8.0 * M * HIDDEN + 8.0 * M
+    out["roofline_hbm_ln"] = {"kernel": "rbf::ln_fwd_kernel<2> (LayerNorm [B*T,256] -> bf16 hi/lo planes)", "bound": "hbm",
+                              "achieved": nbytes / sec / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                              "frac": nbytes / sec / 1e9 / pk["hbm"], "traffic": None, "algorithmic_bytes_per_launch": nbytes,
+                              "launch_ms": sec * 1e3}
     return out
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the fc2-forward
+# GEMM (profiles/r1_ncu_gemm_bf_*.summary.txt); algorithmic bytes of that launch: 421 MB planes + 105 MB output.
+NCU_TRAFFIC = {"bf16x3": 511.0e6, "bf16": None, "fp32": None}
 
 
 def run_product(args, rank: int, world: int, local_rank: int):
@@ -311,7 +350,8 @@ def run_product(args, rank: int, world: int, local_rank: int):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": {"fp32": "f32", "bf16x3": "bf16x3 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate"}[
+            args.precision], "data": "synthetic",
         "config": {"workload": f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, random-split shape "
                                f"(BASELINE configs[1]/[2]), {B} crystals per GPU", "crystals_per_gpu": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "mean_nodes_per_batch": n_nodes,
@@ -324,6 +364,22 @@ def run_product(args, rank: int, world: int, local_rank: int):
     }
     fl = 3.0 * B * flops_per_crystal_fwd(n_nodes / B, n_edges / B, nmax)
     line["model_tflops"] = fl * args.steps / sec / 1e12
+    if world == 1 and args.precision == "bf16x3" and not args.no_alt:
+        # the same step with plain bf16 operands (hi plane only), for reference: stated tolerance 5e-2 on gradients
+        model.precision = "bf16"
+        for i in range(3):
+            step(resident[i % NB])
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(st)
+        for i in range(args.steps):
+            step(resident[i % NB])
+        a1.record(st)
+        torch.cuda.synchronize()
+        alt = a0.elapsed_time(a1) * 1e-3
+        line["bf16_mode"] = {"value": B * args.steps / alt, "unit": UNIT, "ms_per_step": alt / args.steps * 1e3,
+                             "precision": PREC_DESC["bf16"]}
+        model.precision = args.precision
     if world == 1:
         try:
             line.update(kernel_rooflines(B, pk, args.precision))
@@ -331,10 +387,11 @@ def run_product(args, rank: int, world: int, local_rank: int):
             line["roofline"] = {"error": repr(ex)}
         if not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            val, ms, total = cpu_port_throughput(args.cpu_sample, 2, 1, threads)
+            val, ms, total = cpu_port_throughput(args.cpu_sample, args.cpu_steps, 1, threads)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": f"{args.cpu_sample} crystals/step of the same generator, median of 2 steps "
-                                              f"after 1 warm-up ({total:.1f} s of CPU work), oracle/dost_oracle.py"}
+                                    "sample": f"{args.cpu_sample} crystals/step of the same generator, median of "
+                                              f"{args.cpu_steps} fwd+bwd steps after 1 warm-up ({total:.1f} s of CPU work), "
+                                              "oracle/dost_oracle.py (torch CPU restatement of the reference)"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -353,8 +410,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--batch", type=int, default=512, help="crystals per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=16, help="crystals per step of the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=64, help="crystals per step of the CPU baseline sample")
+    ap.add_argument("--cpu-steps", type=int, default=20, help="timed CPU baseline steps (bounded sample, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra bf16-mode measurement")
     ap.add_argument("--precision", default=os.environ.get("DOST_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="GEMM path: fp32 FMA pipe | tcgen05 bf16x3 (fp32 parity, default) | tcgen05 bf16")
     args = ap.parse_args()
