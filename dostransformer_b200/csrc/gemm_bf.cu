@@ -19,6 +19,7 @@
 // land in the canonical UMMA SWIZZLE_128B layouts, so nothing is ever transposed in memory.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace dost {
@@ -33,6 +34,7 @@ constexpr int kSmemBudget = 225 * 1024;         // stages + staging (+ 1 KB alig
 
 struct Maps {
   CUtensorMap a_hi[3], a_lo[3], b_hi, b_lo;
+  CUtensorMap b_hi2, b_lo2;      // K-major B with a 128-row box (CTA pair: each CTA stages half of the 256 output columns)
 };
 
 struct Params {
@@ -103,6 +105,48 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr)
       : "memory");
 }
+// ---- cta_group::2 (CTA pair) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(cluster_bar)
+      : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
@@ -122,9 +166,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-__device__ __forceinline__ uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, bool a_mn, bool b_mn) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -144,14 +188,15 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 struct TileInfo {
   int m0, n0, kbeg, kend, nkt, z;
 };
-template <int BN>
-__device__ __forceinline__ TileInfo tile_info(const Params& p, int tile) {
+// CTA2: a tile is 256 x BN, owned by a CTA pair; CTA `rank` holds rows m0 .. m0+127 (m0 includes 128 * rank).
+template <int BN, bool CTA2>
+__device__ __forceinline__ TileInfo tile_info(const Params& p, int tile, int rank) {
   TileInfo t;
   const int per_z = p.m_tiles * p.n_tiles;
   t.z = tile / per_z;
   const int rem = tile - t.z * per_z;
   const int mt = rem / p.n_tiles, nt = rem - mt * p.n_tiles;
-  t.m0 = mt * BM;
+  t.m0 = mt * (CTA2 ? 2 * BM : BM) + rank * BM;
   t.n0 = nt * BN;
   t.kbeg = 0;
   t.kend = p.K;
@@ -163,10 +208,11 @@ __device__ __forceinline__ TileInfo tile_info(const Params& p, int tile) {
   return t;
 }
 
-template <int NSPLIT, int BN>
+template <int NSPLIT, int BN, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_constant__ Maps maps, const Params p) {
   constexpr bool SPLIT = NSPLIT == 3;
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr int BNL = CTA2 ? BN / 2 : BN;          // B rows (output columns) this CTA stages per k-tile
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2;
   constexpr int STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
   constexpr int NSTAGE_RAW = (kSmemBudget - kEpiBytes) / STAGE_BYTES;
   constexpr int NSTAGE = NSTAGE_RAW < kMaxStages ? NSTAGE_RAW : kMaxStages;
@@ -181,6 +227,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[kMaxStages]);
   const uint32_t accf0 = smem_u32(&bars[2 * kMaxStages]), acce0 = smem_u32(&bars[2 * kMaxStages + 2]);
+  // CTA pair: rank 0 (leader) issues the MMAs for both CTAs; the full / accumulator-empty barriers that the MMA warp
+  // waits on live in the leader and are signalled remotely by the peer's TMA loads / epilogue warps; the empty /
+  // accumulator-full barriers are per CTA and signalled by multicast tcgen05.commit.
+  const int rank = CTA2 ? (int)cluster_ctarank() : 0;
+  const int tile0 = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -189,17 +241,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf0 + 8 * b, 1);
-      mbar_init(acce0 + 8 * b, kEpiWarps);
+      mbar_init(acce0 + 8 * b, CTA2 ? 2 * kEpiWarps : kEpiWarps);
     }
     fence_barrier_init();
   }
   if (warp == kEpiWarps) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   const bool a_mc = p.a_mc != 0, b_mc = p.b_mc != 0;
@@ -209,36 +268,43 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileInfo t = tile_info<BN>(p, tile);
+      for (int tile = tile0; tile < p.total_tiles; tile += tile_step) {
+        const TileInfo t = tile_info<BN, CTA2>(p, tile, rank);
+        const int nb0 = t.n0 + rank * BNL;       // first B row (output column) staged by this CTA
         int seg = 0;
         for (int kt = 0; kt < t.nkt; ++kt) {
           const int k0 = t.kbeg + kt * BK;
           while (seg + 1 < p.a_nseg && k0 >= p.a_kend[seg]) ++seg;
           const int kseg = k0 - (seg == 0 ? 0 : p.a_kend[seg - 1]);   // k inside the segment's own planes
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t bar = full0 + 8 * stage;
-          mbar_expect_tx(bar, STAGE_BYTES);
+          // CTA pair: both CTAs' loads complete on the leader's barrier, which expects the bytes of both
+          const uint32_t bar = CTA2 ? mapa_rank(full0 + 8 * stage, 0) : full0 + 8 * stage;
+          if (!CTA2) mbar_expect_tx(bar, STAGE_BYTES);
+          else if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
+          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
+            if (CTA2) tma_load_2d_2cta(dst, m, c0, c1, bar);
+            else tma_load_2d(dst, m, c0, c1, bar);
+          };
           if (!a_mc) {
-            tma_load_2d(sA, &maps.a_hi[seg], kseg, t.m0, bar);
-            if (SPLIT) tma_load_2d(sA + A_BYTES, &maps.a_lo[seg], kseg, t.m0, bar);
+            load(sA, &maps.a_hi[seg], kseg, t.m0);
+            if (SPLIT) load(sA + A_BYTES, &maps.a_lo[seg], kseg, t.m0);
           } else {
 #pragma unroll
             for (int b = 0; b < BM / 64; ++b) {
-              tma_load_2d(sA + b * 8192, &maps.a_hi[0], t.m0 + 64 * b, k0, bar);
-              if (SPLIT) tma_load_2d(sA + A_BYTES + b * 8192, &maps.a_lo[0], t.m0 + 64 * b, k0, bar);
+              load(sA + b * 8192, &maps.a_hi[0], t.m0 + 64 * b, k0);
+              if (SPLIT) load(sA + A_BYTES + b * 8192, &maps.a_lo[0], t.m0 + 64 * b, k0);
             }
           }
           if (!b_mc) {
-            tma_load_2d(sB, &maps.b_hi, k0, t.n0, bar);
-            if (SPLIT) tma_load_2d(sB + B_BYTES, &maps.b_lo, k0, t.n0, bar);
+            load(sB, CTA2 ? &maps.b_hi2 : &maps.b_hi, k0, nb0);
+            if (SPLIT) load(sB + B_BYTES, CTA2 ? &maps.b_lo2 : &maps.b_lo, k0, nb0);
           } else {
 #pragma unroll
-            for (int b = 0; b < BN / 64; ++b) {
-              tma_load_2d(sB + b * 8192, &maps.b_hi, t.n0 + 64 * b, k0, bar);
-              if (SPLIT) tma_load_2d(sB + B_BYTES + b * 8192, &maps.b_lo, t.n0 + 64 * b, k0, bar);
+            for (int b = 0; b < BNL / 64; ++b) {
+              load(sB + b * 8192, &maps.b_hi, nb0 + 64 * b, k0);
+              if (SPLIT) load(sB + B_BYTES + b * 8192, &maps.b_lo, nb0 + 64 * b, k0);
             }
           }
           if (++stage == NSTAGE) {
@@ -250,15 +316,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     }
   } else if (warp == kEpiWarps) {
     // ============================================================== MMA issuer
-    const uint32_t idesc = make_idesc(BN, a_mc, b_mc);
+    const uint32_t idesc = make_idesc(CTA2 ? 2 * BM : BM, BN, a_mc, b_mc);
     const uint32_t a_kstep = a_mc ? (2048 >> 4) : (32 >> 4);   // descriptor start-address advance per K = 16
     const uint32_t b_kstep = b_mc ? (2048 >> 4) : (32 >> 4);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t acc_phase[2] = {0, 0};
     int local = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-      const TileInfo t = tile_info<BN>(p, tile);
+    for (int tile = tile0; tile < p.total_tiles && rank == 0; tile += tile_step, ++local) {
+      const TileInfo t = tile_info<BN, CTA2>(p, tile, rank);
       const int buf = local & 1;
       mbar_wait(acce0 + 8 * buf, acc_phase[buf] ^ 1);
       tc_fence_after();
@@ -275,16 +341,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           for (int ks = 0; ks < BK / 16; ++ks) {
             const uint64_t a_adv = static_cast<uint64_t>(ks * a_kstep), b_adv = static_cast<uint64_t>(ks * b_kstep);
             const uint32_t first = (kt > 0 || ks > 0) ? 1u : 0u;
+            auto mma = [&](uint64_t da, uint64_t db, uint32_t acc) {
+              if (CTA2) umma_f16_2cta(tmem_d, da, db, idesc, acc);
+              else umma_f16(tmem_d, da, db, idesc, acc);
+            };
             if (SPLIT) {
-              umma_f16(tmem_d, dAlo + a_adv, dBhi + b_adv, idesc, first);
-              umma_f16(tmem_d, dAhi + a_adv, dBlo + b_adv, idesc, 1u);
-              umma_f16(tmem_d, dAhi + a_adv, dBhi + b_adv, idesc, 1u);
+              mma(dAlo + a_adv, dBhi + b_adv, first);
+              mma(dAhi + a_adv, dBlo + b_adv, 1u);
+              mma(dAhi + a_adv, dBhi + b_adv, 1u);
             } else {
-              umma_f16(tmem_d, dAhi + a_adv, dBhi + b_adv, idesc, first);
+              mma(dAhi + a_adv, dBhi + b_adv, first);
             }
           }
-          umma_commit(empty0 + 8 * stage);
-          if (kt == t.nkt - 1) umma_commit(accf0 + 8 * buf);
+          if (CTA2) {
+            umma_commit_2cta(empty0 + 8 * stage);
+            if (kt == t.nkt - 1) umma_commit_2cta(accf0 + 8 * buf);
+          } else {
+            umma_commit(empty0 + 8 * stage);
+            if (kt == t.nkt - 1) umma_commit(accf0 + 8 * buf);
+          }
         }
         __syncwarp();
         if (++stage == NSTAGE) {
@@ -292,7 +367,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           phase ^= 1;
         }
       }
-      if (t.nkt == 0 && lane == 0) umma_commit(accf0 + 8 * buf);
+      if (t.nkt == 0 && lane == 0) {
+        if (CTA2) umma_commit_2cta(accf0 + 8 * buf);
+        else umma_commit(accf0 + 8 * buf);
+      }
       acc_phase[buf] ^= 1;
     }
   } else {
@@ -306,8 +384,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     const int quad = warp & 3, half = warp >> 2;
     const uint32_t stg = smem_u32(epi_smem) + warp * 4096;  // this warp's 32 x 32 fp32 staging tile (128-byte rows)
     const int rsub = lane >> 3, cj = lane & 7;             // after the transpose: rows rsub + 4 i, 16-byte column chunk cj
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-      const TileInfo t = tile_info<BN>(p, tile);
+    const uint32_t acce_remote0 = CTA2 ? mapa_rank(acce0, 0) : 0u;   // the leader's accumulator-empty barriers
+    for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++local) {
+      const TileInfo t = tile_info<BN, CTA2>(p, tile, rank);
       const int buf = local & 1;
       mbar_wait(accf0 + 8 * buf, acc_phase[buf]);
       acc_phase[buf] ^= 1;
@@ -329,7 +408,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         } else {                                           // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+          if (lane == 0) {
+            if (CTA2) mbar_arrive_cluster(acce_remote0 + 8 * buf);
+            else mbar_arrive(acce0 + 8 * buf);
+          }
         }
         __syncwarp();
         float v[8][4];
@@ -439,9 +521,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();     // the peer may still be signalling this CTA's barriers / reading its operands
   if (warp == kEpiWarps) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -539,14 +623,14 @@ static int make_map(CUtensorMap* m, const void* base, long long inner, long long
   return DOST_OK;
 }
 
-template <int NSPLIT, int BN>
+template <int NSPLIT, int BN, bool CTA2>
 static int launch(const Maps& maps, const Params& p, cudaStream_t st) {
-  constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
+  constexpr int A_BYTES = BM * BK * 2, B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
   constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
   constexpr int NSTAGE_RAW = (kSmemBudget - kEpiBytes) / STAGE_BYTES;
   constexpr int NSTAGE = NSTAGE_RAW < kMaxStages ? NSTAGE_RAW : kMaxStages;
   const int smem = NSTAGE * STAGE_BYTES + kEpiBytes + 1024;
-  auto kern = gemm_bf_kernel<NSPLIT, BN>;
+  auto kern = gemm_bf_kernel<NSPLIT, BN, CTA2>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -556,9 +640,40 @@ static int launch(const Maps& maps, const Params& p, cudaStream_t st) {
     }
     configured = true;
   }
-  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, kThreads, smem, st>>>(maps, p);
-  return check_launch("gemm_bf16");
+  if (!CTA2) {
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    kern<<<grid, kThreads, smem, st>>>(maps, p);
+    return check_launch("gemm_bf16");
+  }
+  // CTA pairs: clusters of 2 along x, one pair per 256-row tile, persistent over the tiles
+  const int pairs = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, maps, p);
+  if (e != cudaSuccess) {
+    set_error("gemm_bf16: cluster launch failed: %s", cudaGetErrorString(e));
+    return DOST_ERR_LAUNCH;
+  }
+  return check_launch("gemm_bf16 (CTA pairs)");
+}
+
+// CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles) for the large problems; DOST_GEMM_2CTA=0 disables them.
+static bool use_cta_pairs(int M, int N) {
+  static const int enabled = [] {
+    const char* e = getenv("DOST_GEMM_2CTA");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  return enabled && M >= 256 && N > 128;
 }
 
 static inline bool al16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
@@ -572,6 +687,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   const int nseg = a_mc ? 1 : h->a_nseg;
   DOST_REQUIRE(nseg >= 1 && nseg <= 3, "gemm_bf16: a_nseg must be 1..3");
   const int bn = h->N <= 64 ? 64 : (h->N <= 128 ? 128 : 256);
+  const bool pairs = use_cta_pairs(h->M, h->N);
 
   Maps maps;
   Params p;
@@ -609,15 +725,19 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     DOST_REQUIRE(pl.hi && (!split3 || pl.lo), "gemm_bf16: B planes missing");
     DOST_REQUIRE(al16(pl.hi) && al16(pl.lo) && pl.ld % 8 == 0, "gemm_bf16: B planes must be 16-byte aligned, ld %% 8 == 0");
     int rc;
-    if (!b_mc) {       // [N rows, K] K-major: box {64 k, bn rows}
+    if (!b_mc) {       // [N rows, K] K-major: box {64 k, bn rows} (and {64 k, 128 rows} for CTA pairs)
       rc = make_map(&maps.b_hi, pl.hi, h->K, h->N, pl.ld, bn);
       if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, h->N, pl.ld, bn);
+      if (rc == DOST_OK && pairs) rc = make_map(&maps.b_hi2, pl.hi, h->K, h->N, pl.ld, 128);
+      if (rc == DOST_OK && pairs && split3) rc = make_map(&maps.b_lo2, pl.lo, h->K, h->N, pl.ld, 128);
     } else {           // [K rows, N] MN-major
       rc = make_map(&maps.b_hi, pl.hi, h->N, h->K, pl.ld, 64);
       if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->N, h->K, pl.ld, 64);
     }
     if (rc != DOST_OK) return rc;
     if (!split3) maps.b_lo = maps.b_hi;
+    if (!pairs || b_mc) maps.b_hi2 = maps.b_hi;
+    if (!pairs || b_mc || !split3) maps.b_lo2 = maps.b_hi2;
   }
   const int split = h->split_k < 1 ? 1 : h->split_k;
   p.zmode = split > 1 ? 2 : 0;
@@ -635,7 +755,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     p.kchunk = ((kchunk + BK - 1) / BK) * BK;     // slices end on k-tile boundaries (TMA fetches whole k-tiles)
     p.ws = (float*)workspace;
   }
-  p.m_tiles = (h->M + BM - 1) / BM;
+  p.m_tiles = pairs ? (h->M + 2 * BM - 1) / (2 * BM) : (h->M + BM - 1) / BM;
   p.n_tiles = (h->N + bn - 1) / bn;
   const long long total = (long long)p.m_tiles * p.n_tiles * split;
   DOST_REQUIRE(total <= 0x7fffffffLL, "gemm_bf16: too many tiles");
@@ -662,10 +782,14 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
                "gemm_bf16: output plane alignment");
 
   int rc;
-  if (split3) {
-    rc = bn == 64 ? launch<3, 64>(maps, p, st) : (bn == 128 ? launch<3, 128>(maps, p, st) : launch<3, 256>(maps, p, st));
+  if (pairs) {
+    rc = split3 ? launch<3, 256, true>(maps, p, st) : launch<1, 256, true>(maps, p, st);
+  } else if (split3) {
+    rc = bn == 64 ? launch<3, 64, false>(maps, p, st)
+                  : (bn == 128 ? launch<3, 128, false>(maps, p, st) : launch<3, 256, false>(maps, p, st));
   } else {
-    rc = bn == 64 ? launch<1, 64>(maps, p, st) : (bn == 128 ? launch<1, 128>(maps, p, st) : launch<1, 256>(maps, p, st));
+    rc = bn == 64 ? launch<1, 64, false>(maps, p, st)
+                  : (bn == 128 ? launch<1, 128, false>(maps, p, st) : launch<1, 256, false>(maps, p, st));
   }
   if (rc != DOST_OK) return rc;
   if (split > 1) {
