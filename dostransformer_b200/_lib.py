@@ -60,6 +60,8 @@ class GemmBf16(C.Structure):
         ("out", C.c_void_p), ("ldc", C.c_longlong), ("accumulate", C.c_int),
         ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("ld_op", C.c_longlong),
         ("split_k", C.c_int), ("precision", C.c_int),
+        ("batch", C.c_int), ("a_bstride", C.c_longlong), ("b_bstride", C.c_longlong), ("c_bstride", C.c_longlong),
+        ("res_bstride", C.c_longlong),
     ]
 
 
@@ -140,7 +142,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 3:
+    if lib.dost_abi_version() != 4:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib

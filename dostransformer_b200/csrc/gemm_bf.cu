@@ -41,7 +41,8 @@ struct Params {
   int M, N, K;
   int a_nseg, a_kend[3];
   int a_mc, b_mc;
-  int zmode, kchunk;            // 0: single, 2: split-K (raw partials to ws)
+  int zmode, kchunk;            // 0: single, 1: batched (z = batch index), 2: split-K (raw partials to ws)
+  long long c_bstride, res_bstride;   // batched: element strides of out / residual between batches
   int m_tiles, n_tiles, total_tiles;
   const float* bias;
   const float* rowbias; long long ld_rowbias; int rowbias_div;
@@ -140,19 +141,22 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
       : "memory");
 }
 // TMA load whose completion is signalled on an mbarrier that may live in the peer CTA of the pair
-__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar) {
+__device__ __forceinline__ void tma_load_3d_2cta(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t cluster_bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(cluster_bar)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(cluster_bar)
       : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+// All operand maps are 3-D {inner, rows, batch} (batch extent 1 for plain GEMMs); a box never spans batches, so rows
+// past the end of a batch are zero-filled like rows past the end of the matrix.
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-      "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
       : "memory");
 }
 
@@ -283,9 +287,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           else if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * STAGE_BYTES);
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
+          const int zb = (p.zmode == 1) ? t.z : 0;
           auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
-            if (CTA2) tma_load_2d_2cta(dst, m, c0, c1, bar);
-            else tma_load_2d(dst, m, c0, c1, bar);
+            if (CTA2) tma_load_3d_2cta(dst, m, c0, c1, zb, bar);
+            else tma_load_3d(dst, m, c0, c1, zb, bar);
           };
           if (!a_mc) {
             load(sA, &maps.a_hi[seg], kseg, t.m0);
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             }
         }
         if (p.residual) {
-          const float* rp = p.residual + (long long)mbase * p.ld_res + n;
+          const float* rp = p.residual + (p.zmode == 1 ? (long long)t.z * p.res_bstride : 0) + (long long)mbase * p.ld_res + n;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (mok[i]) {
@@ -484,7 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             }
         }
         if (p.out) {
-          float* op = p.out + (long long)mbase * p.ldc + n;
+          float* op = p.out + (p.zmode == 1 ? (long long)t.z * p.c_bstride : 0) + (long long)mbase * p.ldc + n;
           if (p.accumulate) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -601,18 +606,24 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor [outer rows, inner elements contiguous], row pitch ld elements; box = {64 inner, box_outer}.
-static int make_map(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld, int box_outer) {
+// bf16 tensor [batch][outer rows][inner elements contiguous], row pitch ld and batch pitch bstride elements;
+// box = {64 inner, box_outer rows, 1 batch}.
+static int make_map(CUtensorMap* m, const void* base, long long inner, long long outer, long long ld, int box_outer,
+                    long long batch = 1, long long bstride = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("gemm_bf16: cuTensorMapEncodeTiled is not available");
     return DOST_ERR_UNSUPPORTED;
   }
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64u, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  if (batch <= 1 || bstride <= 0) {
+    batch = 1;
+    bstride = outer * ld;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)bstride * 2};
+  cuuint32_t box[3] = {64u, (cuuint32_t)box_outer, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -688,6 +699,12 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   DOST_REQUIRE(nseg >= 1 && nseg <= 3, "gemm_bf16: a_nseg must be 1..3");
   const int bn = h->N <= 64 ? 64 : (h->N <= 128 ? 128 : 256);
   const bool pairs = use_cta_pairs(h->M, h->N);
+  const int batch = h->batch < 1 ? 1 : h->batch;
+  DOST_REQUIRE(!(batch > 1 && h->split_k > 1), "gemm_bf16: batch and split_k are exclusive");
+  DOST_REQUIRE(batch == 1 || (h->a_nseg <= 1 && !h->rowbias && !h->out_pre && !h->dact_hi && !h->out_hi),
+               "gemm_bf16: batched problems support bias / activation / residual / fp32 stores only");
+  DOST_REQUIRE(batch == 1 || (h->a_bstride % 8 == 0 && h->b_bstride % 8 == 0 && h->c_bstride % 4 == 0 && h->res_bstride % 4 == 0),
+               "gemm_bf16: batch strides must keep 16-byte alignment");
 
   Maps maps;
   Params p;
@@ -705,11 +722,12 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     p.a_kend[s] = kacc;
     int rc;
     if (!a_mc) {       // [M rows, width] K-major: box {64 k, 128 rows}
-      rc = make_map(&maps.a_hi[s], pl.hi, width, pl.rows, pl.ld, BM);
-      if (rc == DOST_OK && split3) rc = make_map(&maps.a_lo[s], pl.lo, width, pl.rows, pl.ld, BM);
+      const long long rows = batch > 1 ? h->M : pl.rows;
+      rc = make_map(&maps.a_hi[s], pl.hi, width, rows, pl.ld, BM, batch, h->a_bstride);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.a_lo[s], pl.lo, width, rows, pl.ld, BM, batch, h->a_bstride);
     } else {           // [K rows, M] MN-major: box {64 m, 64 k}
-      rc = make_map(&maps.a_hi[s], pl.hi, h->M, h->K, pl.ld, 64);
-      if (rc == DOST_OK && split3) rc = make_map(&maps.a_lo[s], pl.lo, h->M, h->K, pl.ld, 64);
+      rc = make_map(&maps.a_hi[s], pl.hi, h->M, h->K, pl.ld, 64, batch, h->a_bstride);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.a_lo[s], pl.lo, h->M, h->K, pl.ld, 64, batch, h->a_bstride);
     }
     if (rc != DOST_OK) return rc;
     if (!split3) maps.a_lo[s] = maps.a_hi[s];
@@ -726,13 +744,14 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     DOST_REQUIRE(al16(pl.hi) && al16(pl.lo) && pl.ld % 8 == 0, "gemm_bf16: B planes must be 16-byte aligned, ld %% 8 == 0");
     int rc;
     if (!b_mc) {       // [N rows, K] K-major: box {64 k, bn rows} (and {64 k, 128 rows} for CTA pairs)
-      rc = make_map(&maps.b_hi, pl.hi, h->K, h->N, pl.ld, bn);
-      if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, h->N, pl.ld, bn);
-      if (rc == DOST_OK && pairs) rc = make_map(&maps.b_hi2, pl.hi, h->K, h->N, pl.ld, 128);
-      if (rc == DOST_OK && pairs && split3) rc = make_map(&maps.b_lo2, pl.lo, h->K, h->N, pl.ld, 128);
+      const long long nrows = (pl.rows > 0 && pl.rows < h->N) ? pl.rows : h->N;   // N may be padded past the stored rows
+      rc = make_map(&maps.b_hi, pl.hi, h->K, nrows, pl.ld, bn, batch, h->b_bstride);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, nrows, pl.ld, bn, batch, h->b_bstride);
+      if (rc == DOST_OK && pairs) rc = make_map(&maps.b_hi2, pl.hi, h->K, nrows, pl.ld, 128, batch, h->b_bstride);
+      if (rc == DOST_OK && pairs && split3) rc = make_map(&maps.b_lo2, pl.lo, h->K, nrows, pl.ld, 128, batch, h->b_bstride);
     } else {           // [K rows, N] MN-major
-      rc = make_map(&maps.b_hi, pl.hi, h->N, h->K, pl.ld, 64);
-      if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->N, h->K, pl.ld, 64);
+      rc = make_map(&maps.b_hi, pl.hi, h->N, h->K, pl.ld, 64, batch, h->b_bstride);
+      if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->N, h->K, pl.ld, 64, batch, h->b_bstride);
     }
     if (rc != DOST_OK) return rc;
     if (!split3) maps.b_lo = maps.b_hi;
@@ -740,7 +759,9 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     if (!pairs || b_mc || !split3) maps.b_lo2 = maps.b_hi2;
   }
   const int split = h->split_k < 1 ? 1 : h->split_k;
-  p.zmode = split > 1 ? 2 : 0;
+  p.zmode = split > 1 ? 2 : (batch > 1 ? 1 : 0);
+  p.c_bstride = h->c_bstride;
+  p.res_bstride = h->res_bstride;
   p.kchunk = 0;
   p.ws = nullptr;
   if (split > 1) {
@@ -757,7 +778,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   }
   p.m_tiles = pairs ? (h->M + 2 * BM - 1) / (2 * BM) : (h->M + BM - 1) / BM;
   p.n_tiles = (h->N + bn - 1) / bn;
-  const long long total = (long long)p.m_tiles * p.n_tiles * split;
+  const long long total = (long long)p.m_tiles * p.n_tiles * (batch > 1 ? batch : split);
   DOST_REQUIRE(total <= 0x7fffffffLL, "gemm_bf16: too many tiles");
   p.total_tiles = (int)total;
   p.bias = h->bias;

@@ -161,8 +161,8 @@ def self_stack(enc: EnergyEncoderParams, x0, seeds: _Seeds):
     x = x0
     for li, layer in enumerate(enc.layers):
         ln0 = layer.layer_norms[0]
-        k = ops.layer_norm(x0, ln0.weight, ln0.bias)
-        q = k if li == 0 else ops.layer_norm(x, ln0.weight, ln0.bias)
+        k = ops.layer_norm(x0, ln0.weight, ln0.bias, want_planes=True)
+        q = k if li == 0 else ops.layer_norm(x, ln0.weight, ln0.bias, want_planes=True)
         y = ops.self_attention(q, k, x, seeds.p, seeds.next())
         x = _ffn(layer, y.view(S * T, H)).view(S, T, H)
     return ops.layer_norm(x, enc.layer_norm.weight, enc.layer_norm.bias)

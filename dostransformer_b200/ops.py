@@ -303,8 +303,10 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
                 prelu_slope: Optional[torch.Tensor] = None, out_pre: Optional[torch.Tensor] = None,
                 dact: Optional[Planes] = None, dact_slope: float = 0.0, residual: Optional[torch.Tensor] = None,
                 accumulate: bool = False, split_k: int = 1, out_planes: Optional[Planes] = None,
-                ldc: Optional[int] = None, prec: Optional[int] = None) -> None:
-    """C = epi(A B^T) on the TMA-fed tcgen05 kernel; operands are bf16 planes (see include/dost.h)."""
+                ldc: Optional[int] = None, prec: Optional[int] = None, batch: int = 1, a_bstride: int = 0, b_bstride: int = 0,
+                c_bstride: int = 0, res_bstride: int = 0, ld_res: Optional[int] = None, b_rows: Optional[int] = None) -> None:
+    """C = epi(A B^T) on the TMA-fed tcgen05 kernel; operands are bf16 planes (see include/dost.h).
+    b_rows: valid rows of a K-major B per problem when N is padded beyond them (the rest reads as zero)."""
     g = L.GemmBf16()
     g.M, g.N, g.K = M, N, K
     g.a_mode, g.a_nseg = a_mode, len(a)
@@ -312,6 +314,7 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
         g.a[i] = _planes_c(pl, pl.cols if a_mode == L.KC else K)
     g.b_mode = b_mode
     g.b = _planes_c(b, 0)
+    g.b.rows = b_rows if b_rows is not None else 0
     g.bias = bias.data_ptr() if bias is not None else None
     if rowbias is not None:
         g.rowbias, g.ld_rowbias, g.rowbias_div = rowbias.data_ptr(), _ld(rowbias), rowbias_div
@@ -322,11 +325,12 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
     if dact is not None:
         g.dact_hi, g.ld_dact, g.dact_slope = dact.hi.data_ptr(), dact.ld, dact_slope
     if residual is not None:
-        g.residual, g.ld_res = residual.data_ptr(), _ld(residual)
+        g.residual, g.ld_res = residual.data_ptr(), (ld_res if ld_res is not None else _ld(residual))
     if out is not None:
         g.out = out.data_ptr()
         g.ldc = ldc if ldc is not None else _ld(out)
     g.accumulate = 1 if accumulate else 0
+    g.batch, g.a_bstride, g.b_bstride, g.c_bstride, g.res_bstride = batch, a_bstride, b_bstride, c_bstride, res_bstride
     if out_planes is not None:
         g.out_hi = out_planes.hi.data_ptr()
         g.out_lo = out_planes.lo.data_ptr() if out_planes.lo is not None else None
@@ -931,18 +935,26 @@ def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: to
 # =====================================================================================================
 class _LayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gamma, beta, slope):
+    def forward(ctx, x, gamma, beta, slope, want_planes=False):
         x2 = x.reshape(-1, x.shape[-1])
         if x2.stride(-1) != 1:
             x2 = x2.contiguous()
         M, W = x2.shape
         ctx.vec = x.dtype == torch.float32 and planes_ok(W) and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0 \
             and not os.environ.get("DOST_NO_LNVEC")
+        ctx.with_planes = False
         if ctx.vec:       # 16-byte vectorised fp32 kernels (rows_bf.cu)
-            y, _, stats = ln_fwd_planes(x2, gamma, beta, slope, want_y=True, want_planes=False)
+            y, pl, stats = ln_fwd_planes(x2, gamma, beta, slope, want_y=True, want_planes=want_planes)
             ctx.save_for_backward(x2, gamma, beta, slope, stats)
             ctx.shape = x.shape
+            if want_planes:
+                ctx.with_planes = True
+                lo = pl.lo if pl.lo is not None else pl.hi
+                ctx.mark_non_differentiable(pl.hi, lo)
+                ctx.set_materialize_grads(False)
+                return y.view(x.shape), pl.hi, lo
             return y.view(x.shape)
+        assert not want_planes
         y = torch.empty(M, W, dtype=x.dtype, device=x.device)
         stats = torch.empty(M, 2, dtype=x.dtype, device=x.device)
         L.check(L.lib().dost_ln_fwd(L.dt(x), L.p(x2), _ld(x2), L.p(gamma), L.p(beta), L.p(slope), L.p(y), L.p(stats), M, W,
@@ -952,7 +964,7 @@ class _LayerNorm(torch.autograd.Function):
         return y.view(x.shape)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, *_unused):
         x2, gamma, beta, slope, stats = ctx.saved_tensors
         M, W = x2.shape
         dy2 = dy.reshape(M, W)
@@ -960,7 +972,7 @@ class _LayerNorm(torch.autograd.Function):
             dy2 = dy2.contiguous()
         if ctx.vec and dy2.stride(0) % 4 == 0 and dy2.data_ptr() % 16 == 0:
             dx, _, dg, db, ds, _ = ln_bwd_planes(dy2, x2, stats, gamma, beta, slope)
-            return dx.view(ctx.shape), dg, db, ds
+            return dx.view(ctx.shape), dg, db, ds, None
         dev, dtype = x2.device, x2.dtype
         dx = torch.empty(M, W, dtype=dtype, device=dev)
         dg = torch.empty(W, dtype=dtype, device=dev)
@@ -971,11 +983,20 @@ class _LayerNorm(torch.autograd.Function):
         ws = _ws(nb, dev)
         L.check(lib.dost_ln_bwd(L.dt(x2), L.p(dy2), _ld(dy2), L.p(x2), _ld(x2), L.p(stats), L.p(gamma), L.p(beta),
                                 L.p(slope), L.p(dx), L.p(dg), L.p(db), L.p(ds), M, W, L.p(ws), nb, L.stream()), "ln_bwd")
-        return dx.view(ctx.shape), dg, db, ds
+        return dx.view(ctx.shape), dg, db, ds, None
 
 
-def layer_norm(x, gamma, beta, prelu_slope=None):
-    return _LayerNorm.apply(x, gamma, beta, prelu_slope)
+def layer_norm(x, gamma, beta, prelu_slope=None, want_planes: bool = False):
+    """LayerNorm (+PReLU).  want_planes: also emit the result as GEMM operand planes (attached to the returned tensor as
+    ``_dost_planes``; only on the vectorised fp32 path)."""
+    if want_planes and x.dtype == torch.float32 and planes_ok(x.shape[-1]) and tc_active(x) and \
+            not os.environ.get("DOST_NO_LNVEC"):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0:
+            y, hi, lo = _LayerNorm.apply(x, gamma, beta, prelu_slope, True)
+            y._dost_planes = Planes(hi, lo if _with_lo() else None, x2.shape[0], x2.shape[1])
+            return y
+    return _LayerNorm.apply(x, gamma, beta, prelu_slope, False)
 
 
 # =====================================================================================================
@@ -1060,10 +1081,30 @@ class _SelfAttention(torch.autograd.Function):
     def forward(ctx, q, k, resid, drop_p: float, seed: int):
         S, Lq, H = q.shape
         Lk = k.shape[1]
+        qpl, kpl = _planes3(q), _planes3(k)
         q, k, resid = q.contiguous(), k.contiguous(), resid.contiguous()
         dev, dtype = q.device, q.dtype
         Lp = (Lk + 3) // 4 * 4          # padded row length of the score matrices: keeps 16-byte vector loads legal
         scores = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
+        ctx.on_planes = tc_active(q) and H % 8 == 0 and Lq * Lk * H >= (1 << 18) and not os.environ.get("DOST_NO_ATTNPLANES")
+        if ctx.on_planes:
+            # the four batched contractions on the TMA-fed tensor-core kernel (3-D tensor maps, one batch per sequence)
+            qp = qpl if qpl is not None else split_planes(q.view(S * Lq, H))
+            kp = kpl if kpl is not None else split_planes(k.view(S * Lk, H))
+            gemm_planes(M=Lq, N=Lp, K=H, a=[qp], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=scores.view(S * Lq, Lp),
+                        batch=S, a_bstride=Lq * qp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
+            pd = torch.empty_like(scores) if drop_p > 0 else scores
+            L.check(L.lib().dost_softmax_fwd(L.dt(q), L.p(scores), L.p(scores), L.p(pd), S * Lq, Lk, Lp, float(H) ** -0.5,
+                                             drop_p, seed, L.stream()), "softmax_fwd")
+            pdp = _cols(split_planes(pd.view(S * Lq, Lp)), Lk)
+            out = torch.empty(S, Lq, H, dtype=dtype, device=dev)
+            gemm_planes(M=Lq, N=H, K=Lk, a=[pdp], a_mode=L.KC, b=kp, b_mode=L.MC, out=out.view(S * Lq, H),
+                        residual=resid.view(S * Lq, H), batch=S, a_bstride=Lq * pdp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * H,
+                        res_bstride=Lq * H)
+            ctx.save_for_backward(scores, pd if drop_p > 0 else None, *_planes_save(qp), *_planes_save(kp), *_planes_save(pdp))
+            ctx.drop_p, ctx.seed, ctx.prec = drop_p, seed, _PRECISION
+            ctx.dims = (S, Lq, Lk, H, Lp)
+            return out
         gemm_raw(M=Lq, N=Lk, K=H, a=[(q.view(S * Lq, H), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.KC,
                  out=scores, batch=S, a_bstride=Lq * H, b_bstride=Lk * H, c_bstride=Lq * Lp, ldc=Lp)
         pd = torch.empty_like(scores) if drop_p > 0 else scores
@@ -1078,6 +1119,9 @@ class _SelfAttention(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out):
+        if ctx.on_planes:
+            with precision_value(ctx.prec):
+                return _SelfAttention._backward_planes(ctx, d_out)
         q, k, prob, pd = ctx.saved_tensors
         if pd is None:
             pd = prob
@@ -1105,6 +1149,52 @@ class _SelfAttention(torch.autograd.Function):
                  out=dk, accumulate=True, batch=S, a_bstride=Lq * Lp, b_bstride=Lq * H, c_bstride=Lk * H, ldc=H, lda=Lp,
                  prec=ctx.prec)
         return dq, dk, d_out, None, None
+
+
+def _self_attention_backward_planes(ctx, d_out):
+    prob, pd, qh, ql, kh, kl, ph, pl_ = ctx.saved_tensors
+    S, Lq, Lk, H, Lp = ctx.dims
+    dev = prob.device
+    scale = float(H) ** -0.5
+    qp, kp = Planes(qh, ql, S * Lq, H), Planes(kh, kl, S * Lk, H)
+    pdp = Planes(ph, pl_, S * Lq, Lk)
+    d_out = d_out.contiguous()
+    dop = split_planes(d_out.view(S * Lq, H))
+    # dPd = dO k^T
+    dpd = torch.empty(S, Lq, Lp, dtype=torch.float32, device=dev)
+    gemm_planes(M=Lq, N=Lp, K=H, a=[dop], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=dpd.view(S * Lq, Lp), batch=S,
+                a_bstride=Lq * dop.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
+    L.check(L.lib().dost_softmax_bwd(L.F32, L.p(prob), L.p(dpd), L.p(dpd), S * Lq, Lk, Lp, scale, ctx.drop_p, ctx.seed,
+                                     L.stream()), "softmax_bwd")
+    dsp = _cols(split_planes(dpd.view(S * Lq, Lp)), Lk)
+    # dQ = dS k
+    dq = torch.empty(S, Lq, H, dtype=torch.float32, device=dev)
+    gemm_planes(M=Lq, N=H, K=Lk, a=[dsp], a_mode=L.KC, b=kp, b_mode=L.MC, out=dq.view(S * Lq, H), batch=S,
+                a_bstride=Lq * dsp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * H)
+    # dK = dS^T q + Pd^T dO   (reduction over the Lq queries)
+    dk = torch.empty(S, Lk, H, dtype=torch.float32, device=dev)
+    gemm_planes(M=Lk, N=H, K=Lq, a=[dsp], a_mode=L.MC, b=qp, b_mode=L.MC, out=dk.view(S * Lk, H), batch=S,
+                a_bstride=Lq * dsp.ld, b_bstride=Lq * qp.ld, c_bstride=Lk * H)
+    gemm_planes(M=Lk, N=H, K=Lq, a=[pdp], a_mode=L.MC, b=dop, b_mode=L.MC, out=dk.view(S * Lk, H), accumulate=True, batch=S,
+                a_bstride=Lq * pdp.ld, b_bstride=Lq * dop.ld, c_bstride=Lk * H)
+    return dq, dk, d_out, None, None
+
+
+_SelfAttention._backward_planes = staticmethod(_self_attention_backward_planes)
+
+
+def _cols(pl: Planes, cols: int) -> Planes:
+    """Same storage, fewer valid columns (the padded tail is excluded from the tensor-map extent)."""
+    return Planes(pl.hi, pl.lo, pl.rows, cols)
+
+
+def _planes3(t: torch.Tensor) -> Optional[Planes]:
+    """Planes attached to a [S, L, H] tensor by the LayerNorm that produced it."""
+    pl = getattr(t, "_dost_planes", None)
+    if pl is not None and t.dim() == 3 and pl.rows == t.shape[0] * t.shape[1] and pl.cols == t.shape[2] and \
+            (pl.lo is not None) == _with_lo():
+        return pl
+    return None
 
 
 def self_attention(q, k, resid, drop_p: float = 0.0, seed: int = 0):

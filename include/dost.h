@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 3
+#define DOST_ABI_VERSION 4
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -120,7 +120,7 @@ typedef struct {
   const void* hi;    /* bf16 plane */
   const void* lo;    /* bf16 residual plane or NULL */
   long long ld;      /* leading dimension in elements, multiple of 8 */
-  long long rows;    /* rows stored */
+  long long rows;    /* rows stored (B, KC: if 0 < rows < N the missing rows read as zero; 0 means N) */
   int width;         /* valid columns (A, KC: the k-range this segment contributes) */
 } dost_planes_t;
 
@@ -140,6 +140,10 @@ typedef struct {
   void* out_hi; void* out_lo; long long ld_op;
   int split_k;               /* > 1: deterministic split-K (plain fp32 stores only) */
   int precision;             /* DOST_PREC_BF16X3 or DOST_PREC_BF16 */
+  /* batch > 1: independent problems (torch.bmm of the energy self attention, multihead_attention.py:68,72); element
+   * strides between consecutive problems of the A / B planes, of out and of residual.  Exclusive with split_k. */
+  int batch;
+  long long a_bstride, b_bstride, c_bstride, res_bstride;
 } dost_gemm_bf16_t;
 
 size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g);

@@ -724,3 +724,22 @@ def test_edge_block_matches_fp32_path(prec, tol):
     for name, a, b in zip(names, got, want):
         err = ((a.double() - b.double()).norm() / b.double().norm()).item()
         assert err < tol, (name, err)
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 5e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("S,Lq,Lk,H", [(5, 201, 201, 256), (3, 51, 51, 64), (4, 17, 40, 128)])
+def test_dense_attention_on_planes(prec, tol, S, Lq, Lk, H):
+    """The batched contractions of the energy self attention on the TMA-fed tensor-core kernel (3-D tensor maps)."""
+    q, k = _leaf(_rand(S, Lq, H, dtype=torch.float32, seed=1)), _leaf(_rand(S, Lk, H, dtype=torch.float32, seed=2))
+    r = _leaf(_rand(S, Lq, H, dtype=torch.float32, seed=3))
+    with ops.precision(prec):
+        o1, g1 = _grads(lambda: ops.self_attention(q, k, r), [q, k, r])
+    o2, g2 = _grads(lambda: r + O.attention(q, k), [q, k, r])
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol
+    if Lq == Lk:
+        with ops.precision(prec):
+            o1, g1 = _grads(lambda: ops.self_attention(q, q, r), [q, r])
+        o2, g2 = _grads(lambda: r + O.attention(q, q), [q, r])
+        for a_, b_ in zip(o1 + g1, o2 + g2):
+            assert relerr(a_, b_) < tol
