@@ -80,6 +80,9 @@ _SIGNATURES = {
     "dost_gemm_bf16": (C.c_int, [C.POINTER(GemmBf16), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dost_split_planes": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong,
                                     C.c_void_p]),
+    "dost_split_planes_colsum_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int, C.c_longlong]),
+    "dost_split_planes_colsum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "dost_ln_fwd_planes": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
@@ -120,6 +123,10 @@ _SIGNATURES = {
                                    C.c_double, C.c_ulonglong, C.c_void_p]),
     "dost_softmax_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
                                    C.c_double, C.c_ulonglong, C.c_void_p]),
+    "dost_softmax_fwd_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
+                                          C.c_double, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dost_softmax_bwd_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
+                                          C.c_double, C.c_ulonglong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dost_loss_fwd": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
     "dost_loss_bwd": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int,

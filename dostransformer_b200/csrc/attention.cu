@@ -6,6 +6,7 @@
 // One warp per query, lane l owns features l, l+32, ...; keys are staged in shared memory tiles; online
 // softmax in fp32 (the reference forces fp32 softmax even for the float64 phonon model).
 #include <math.h>
+#include <cuda_bf16.h>
 #include "common.cuh"
 
 namespace dost {
@@ -385,7 +386,8 @@ template <typename T, int NPL>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ sc, T* __restrict__ p,
                                                           T* __restrict__ pd, long long rows, int cols, long long ld, T scale,
                                                           unsigned int thresh, float inv_keep,
-                                                          unsigned long long seed) {
+                                                          unsigned long long seed, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo, long long ldp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long r = blockIdx.x * 8LL + warp; r < rows; r += (long long)gridDim.x * 8) {
     const T* sr = sc + r * ld;
@@ -413,10 +415,15 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const T* __restrict__ 
       if (c < cols) {
         const float pr = v[i] * inv;
         p[r * ld + c] = static_cast<T>(pr);
+        float w = pr;
         if (pd != p) {
-          float w = pr;
           if (thresh) w = keep_mask(seed, (unsigned long long)r * cols + c, thresh) ? pr * inv_keep : 0.f;
           pd[r * ld + c] = static_cast<T>(w);
+        }
+        if (hi) {      // the (dropped-out) probabilities as GEMM operand planes
+          const __nv_bfloat16 h = __float2bfloat16_rn(w);
+          hi[r * ldp + c] = h;
+          if (lo) lo[r * ldp + c] = __float2bfloat16_rn(w - __bfloat162float(h));
         }
       }
     }
@@ -427,7 +434,8 @@ template <typename T, int NPL>
 __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ p, const T* __restrict__ dpd,
                                                           T* __restrict__ ds, long long rows, int cols, long long ld, T scale,
                                                           unsigned int thresh, float inv_keep,
-                                                          unsigned long long seed) {
+                                                          unsigned long long seed, __nv_bfloat16* __restrict__ hi,
+                                                          __nv_bfloat16* __restrict__ lo, long long ldp) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long r = blockIdx.x * 8LL + warp; r < rows; r += (long long)gridDim.x * 8) {
     T pv[NPL], dp[NPL];
@@ -450,7 +458,16 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + 32 * i;
-      if (c < cols) ds[r * ld + c] = scale * pv[i] * (dp[i] - dot);
+      if (c < cols) {
+        const T o = scale * pv[i] * (dp[i] - dot);
+        if (ds) ds[r * ld + c] = o;
+        if (hi) {
+          const float of = static_cast<float>(o);
+          const __nv_bfloat16 h = __float2bfloat16_rn(of);
+          hi[r * ldp + c] = h;
+          if (lo) lo[r * ldp + c] = __float2bfloat16_rn(of - __bfloat162float(h));
+        }
+      }
     }
   }
 }
@@ -548,7 +565,8 @@ static int run_xattn_bwd(const void* dO, const void* q, long long q_ss, const vo
 
 template <typename T>
 static int run_softmax(bool fwd, const void* a, void* b, void* c, long long rows, int cols, long long ld, double scale,
-                       double drop_p, unsigned long long seed, cudaStream_t st) {
+                       double drop_p, unsigned long long seed, cudaStream_t st, void* hi = nullptr, void* lo = nullptr,
+                       long long ldp = 0) {
   const unsigned int thresh = drop_p > 0 ? drop_threshold(drop_p) : 0u;
   const float inv_keep = drop_p > 0 ? (float)(1.0 / (1.0 - drop_p)) : 1.f;
   int npl = (cols + 31) / 32, pw = 1;
@@ -558,10 +576,11 @@ static int run_softmax(bool fwd, const void* a, void* b, void* c, long long rows
   case NPL:                                                                                                       \
     if (fwd)                                                                                                      \
       softmax_fwd_kernel<T, NPL><<<blocks, 256, 0, st>>>((const T*)a, (T*)b, (T*)c, rows, cols, ld, (T)scale, thresh, \
-                                                         inv_keep, seed);                                         \
+                                                         inv_keep, seed, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp); \
     else                                                                                                          \
       softmax_bwd_kernel<T, NPL><<<blocks, 256, 0, st>>>((const T*)a, (const T*)b, (T*)c, rows, cols, ld, (T)scale,   \
-                                                         thresh, inv_keep, seed);                                 \
+                                                         thresh, inv_keep, seed, (__nv_bfloat16*)hi,              \
+                                                         (__nv_bfloat16*)lo, ldp);                                \
     break;
   switch (pw) {
     DOST_SM(1) DOST_SM(2) DOST_SM(4) DOST_SM(8) DOST_SM(16) DOST_SM(32)
@@ -641,4 +660,22 @@ extern "C" int dost_softmax_bwd(int dtype, const void* p, const void* dpd, void*
   if (dtype == DOST_F64) return run_softmax<double>(false, p, (void*)dpd, ds, rows, cols, ld, scale, drop_p, seed, st);
   set_error("softmax_bwd: unsupported dtype %d", dtype);
   return DOST_ERR_UNSUPPORTED;
+}
+
+/* fp32 softmax whose (dropped-out) probabilities / score gradients are also written as bf16 hi/lo operand planes
+ * (rows ldp elements apart) for the batched tensor-core GEMMs that consume them. */
+extern "C" int dost_softmax_fwd_planes(const float* s, float* p, float* pd, long long rows, int cols, long long ld, double scale,
+                                       double drop_p, unsigned long long seed, void* hi, void* lo, long long ldp,
+                                       dost_stream_t stream) {
+  DOST_REQUIRE(s && p && hi && rows > 0 && cols > 0 && ld >= cols && ldp >= cols, "softmax_fwd_planes: bad args");
+  if (!pd) pd = p;
+  DOST_REQUIRE(!(drop_p > 0 && pd == p), "softmax_fwd_planes: dropout needs a separate pd buffer");
+  return run_softmax<float>(true, s, p, pd, rows, cols, ld, scale, drop_p, seed, (cudaStream_t)stream, hi, lo, ldp);
+}
+
+extern "C" int dost_softmax_bwd_planes(const float* p, const float* dpd, float* ds, long long rows, int cols, long long ld,
+                                       double scale, double drop_p, unsigned long long seed, void* hi, void* lo, long long ldp,
+                                       dost_stream_t stream) {
+  DOST_REQUIRE(p && dpd && hi && rows > 0 && cols > 0 && ld >= cols && ldp >= cols, "softmax_bwd_planes: bad args");
+  return run_softmax<float>(false, p, (void*)dpd, ds, rows, cols, ld, scale, drop_p, seed, (cudaStream_t)stream, hi, lo, ldp);
 }

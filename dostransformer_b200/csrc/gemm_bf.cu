@@ -589,6 +589,84 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, l
   }
 }
 
+// Same conversion, plus the column sums of x (the bias gradient when x is the gradient of a Linear's output): one pass
+// over x instead of two.  Block = 32 column chunks (256 columns) x 8 row lanes over a contiguous row range; the row
+// lanes are combined through shared memory and the row ranges by colsum_stage2_kernel, both in a fixed order.
+__global__ void __launch_bounds__(256) split_planes_colsum_kernel(const float* __restrict__ x, long long ld, long long rows, int cols,
+                                                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                                                  int ldp, int vec_ok, long long rows_per_chunk,
+                                                                  float* __restrict__ partial) {
+  __shared__ float sm[8][32][9];
+  const int cg = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cg) * 8;
+  const long long rbeg = blockIdx.y * rows_per_chunk, rend = min(rows, rbeg + rows_per_chunk);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < ldp) {
+    for (long long r = rbeg + ry; r < rend; r += 8) {
+      float v[8];
+      const float* src = x + r * ld + c;
+      if (vec_ok && c + 8 <= cols) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? __ldg(src + j) : 0.f;
+      }
+      uint4 h, l;
+      uint32_t* hp = &h.x;
+      uint32_t* lp = &l.x;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hp[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+        lp[j] = pack_bf16(v[2 * j] - __uint_as_float(hp[j] << 16), v[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
+      }
+      *reinterpret_cast<uint4*>(hi + r * ldp + c) = h;
+      if (lo) *reinterpret_cast<uint4*>(lo + r * ldp + c) = l;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ry][cg][j] = acc[j];
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += sm[k][cg][j];
+      if (c + j < cols) partial[(long long)blockIdx.y * cols + c + j] = t;
+    }
+  }
+}
+
+// 32 columns x 8 lanes per block: lane ry sums chunks ry, ry + 8, ...; lanes combined in order (deterministic)
+__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  float s = 0.f;
+  if (c < W)
+    for (int b = ry; b < nchunks; b += 8) s += ws[(long long)b * W + c];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    out[c] = t;
+  }
+}
+
+static inline int split_colsum_chunks(long long rows, int ldp) {
+  const long long gx = (ldp / 8 + 31) / 32;
+  long long nch = (3LL * kNumSMs + gx - 1) / gx;
+  const long long maxch = (rows + 31) / 32;
+  if (nch > maxch) nch = maxch;
+  if (nch < 1) nch = 1;
+  return (int)nch;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -834,6 +912,33 @@ extern "C" size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g) {
 extern "C" int dost_gemm_bf16(const dost_gemm_bf16_t* g, void* workspace, size_t workspace_bytes, dost_stream_t stream) {
   DOST_REQUIRE(g != nullptr, "gemm_bf16: null descriptor");
   return dost::bf::run(g, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" size_t dost_split_planes_colsum_workspace_bytes(long long rows, int cols, long long ldp) {
+  return sizeof(float) * (size_t)dost::bf::split_colsum_chunks(rows, (int)ldp) * cols;
+}
+
+extern "C" int dost_split_planes_colsum(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
+                                        float* colsum, void* workspace, size_t workspace_bytes, dost_stream_t stream) {
+  DOST_REQUIRE(x && hi && colsum, "split_planes_colsum: null pointer");
+  DOST_REQUIRE(rows > 0 && cols > 0 && ldp >= cols && ldp % 8 == 0, "split_planes_colsum: need rows > 0, ldp %% 8 == 0, ldp >= cols");
+  DOST_REQUIRE(((uintptr_t)hi & 15) == 0 && ((uintptr_t)lo & 15) == 0, "split_planes_colsum: planes must be 16-byte aligned");
+  const int nch = dost::bf::split_colsum_chunks(rows, (int)ldp);
+  const size_t need = sizeof(float) * (size_t)nch * cols;
+  if (!workspace || workspace_bytes < need) {
+    dost::set_error("split_planes_colsum: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DOST_ERR_WORKSPACE;
+  }
+  const int vec_ok = (((uintptr_t)x & 15) == 0 && ld % 4 == 0) ? 1 : 0;
+  const long long rpc = (rows + nch - 1) / nch;
+  dim3 grid((unsigned)((ldp / 8 + 31) / 32), nch);
+  cudaStream_t st = (cudaStream_t)stream;
+  dost::bf::split_planes_colsum_kernel<<<grid, 256, 0, st>>>(x, ld, rows, cols, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, (int)ldp, vec_ok,
+                                                             rpc, (float*)workspace);
+  int rc = dost::check_launch("split_planes_colsum");
+  if (rc != DOST_OK) return rc;
+  dost::bf::colsum_stage2_kernel<<<dost::ceil_div(cols, 32), 256, 0, st>>>((const float*)workspace, nch, cols, colsum);
+  return dost::check_launch("split_planes_colsum stage2");
 }
 
 extern "C" int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,

@@ -290,12 +290,21 @@ __global__ void __launch_bounds__(256) colsum_planes_kernel(const __nv_bfloat16*
   }
 }
 
-__global__ void colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= W) return;
+__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float s = 0.f;
-  for (int b = 0; b < nchunks; ++b) s += ws[(long long)b * W + c];
-  out[c] = s;
+  if (c < W)
+    for (int b = ry; b < nchunks; b += 8) s += ws[(long long)b * W + c];
+  sm[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    out[c] = t;
+  }
 }
 
 static inline int bwd_blocks(long long M) {
@@ -409,6 +418,6 @@ extern "C" int dost_colsum_planes(const void* hi, const void* lo, long long ld, 
                                                   (float*)workspace);
   int rc = check_launch("colsum_planes stage1");
   if (rc != DOST_OK) return rc;
-  rbf::colsum_stage2_kernel<<<ceil_div(W, 256), 256, 0, st>>>((const float*)workspace, nch, W, out);
+  rbf::colsum_stage2_kernel<<<ceil_div(W, 32), 256, 0, st>>>((const float*)workspace, nch, W, out);
   return check_launch("colsum_planes stage2");
 }

@@ -272,6 +272,22 @@ def split_planes(x2d: torch.Tensor, with_lo: Optional[bool] = None) -> Planes:
     return pl
 
 
+def split_planes_colsum(x2d: torch.Tensor) -> Tuple[Planes, torch.Tensor]:
+    """split_planes(x) and x.sum(0) in one pass over x (operand planes of an output gradient + its bias gradient)."""
+    assert x2d.dtype == torch.float32 and x2d.dim() == 2
+    if x2d.stride(1) != 1:
+        x2d = x2d.contiguous()
+    rows, cols = x2d.shape
+    pl = empty_planes(rows, cols, x2d.device, _with_lo())
+    cs = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+    lib = L.lib()
+    nb = lib.dost_split_planes_colsum_workspace_bytes(rows, cols, pl.ld)
+    ws = _ws(nb, x2d.device)
+    L.check(lib.dost_split_planes_colsum(L.p(x2d), _ld(x2d), rows, cols, L.p(pl.hi), L.p(pl.lo), pl.ld, L.p(cs), L.p(ws), nb,
+                                         L.stream()), "split_planes_colsum")
+    return pl, cs
+
+
 def weight_planes(w: torch.Tensor) -> Planes:
     """Planes of a parameter (or of a strided view of one), cached ON the parameter object until it is modified in
     place (optimizer step).  Keying on the object - not on its address - keeps the cache exact across models."""
@@ -458,8 +474,7 @@ class _FFNBlock(torch.autograd.Function):
             h0p, h1p = _planes_load(h0h, h0l, M, H), _planes_load(h1h, h1l, M, F)
             w1p, w2p = weight_planes(w1), weight_planes(w2)
             d_out = d_out.contiguous()
-            dop = split_planes(d_out)
-            db2 = colsum(d_out)
+            dop, db2 = split_planes_colsum(d_out)
             dw2 = torch.empty(H, F, dtype=torch.float32, device=dev)
             gemm_planes(M=H, N=F, K=M, a=[dop], a_mode=L.MC, b=h1p, b_mode=L.MC, out=dw2, split_k=_split_for(H, F, M))
             # d(relu input) = (d_out W2) * relu'(h1): relu' from the sign of the saved hi plane, result as planes only
@@ -556,8 +571,7 @@ class _EdgeBlock(torch.autograd.Function):
             else:
                 dv = torch.empty(E, H, dtype=torch.float32, device=dev)
                 _axpy2(d_v.contiguous(), d_e_new.contiguous(), dv)
-            dvp = split_planes(dv)
-            db2 = colsum(dv)
+            dvp, db2 = split_planes_colsum(dv)
             dw2 = torch.empty(H, W, dtype=torch.float32, device=dev)
             gemm_planes(M=H, N=W, K=E, a=[dvp], a_mode=L.MC, b=h2p, b_mode=L.MC, out=dw2, split_k=_split_for(H, W, E))
             dh2 = torch.empty(E, W, dtype=torch.float32, device=dev)
@@ -804,8 +818,10 @@ class _Linear(torch.autograd.Function):
         d_res = d_out if ctx.has_res else None
         dv, d_slope = _Linear._dv(ctx, spec, slope, saved_act, d_out, d_pre)
         needs = ctx.needs_input_grad
-        dvp = split_planes(dv)
-        d_bias = colsum(dv) if (ctx.has_bias and needs[2]) else None
+        if ctx.has_bias and needs[2]:
+            dvp, d_bias = split_planes_colsum(dv)
+        else:
+            dvp, d_bias = split_planes(dv), None
         d_rowbias = None
         if ctx.has_rowbias and needs[5]:
             div = spec.rowbias_div
@@ -1094,9 +1110,9 @@ class _SelfAttention(torch.autograd.Function):
             gemm_planes(M=Lq, N=Lp, K=H, a=[qp], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=scores.view(S * Lq, Lp),
                         batch=S, a_bstride=Lq * qp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
             pd = torch.empty_like(scores) if drop_p > 0 else scores
-            L.check(L.lib().dost_softmax_fwd(L.dt(q), L.p(scores), L.p(scores), L.p(pd), S * Lq, Lk, Lp, float(H) ** -0.5,
-                                             drop_p, seed, L.stream()), "softmax_fwd")
-            pdp = _cols(split_planes(pd.view(S * Lq, Lp)), Lk)
+            pdp = empty_planes(S * Lq, Lk, dev, _with_lo())      # probabilities straight into operand planes
+            L.check(L.lib().dost_softmax_fwd_planes(L.p(scores), L.p(scores), L.p(pd), S * Lq, Lk, Lp, float(H) ** -0.5, drop_p,
+                                                    seed, L.p(pdp.hi), L.p(pdp.lo), pdp.ld, L.stream()), "softmax_fwd_planes")
             out = torch.empty(S, Lq, H, dtype=dtype, device=dev)
             gemm_planes(M=Lq, N=H, K=Lk, a=[pdp], a_mode=L.KC, b=kp, b_mode=L.MC, out=out.view(S * Lq, H),
                         residual=resid.view(S * Lq, H), batch=S, a_bstride=Lq * pdp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * H,
@@ -1164,9 +1180,9 @@ def _self_attention_backward_planes(ctx, d_out):
     dpd = torch.empty(S, Lq, Lp, dtype=torch.float32, device=dev)
     gemm_planes(M=Lq, N=Lp, K=H, a=[dop], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=dpd.view(S * Lq, Lp), batch=S,
                 a_bstride=Lq * dop.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
-    L.check(L.lib().dost_softmax_bwd(L.F32, L.p(prob), L.p(dpd), L.p(dpd), S * Lq, Lk, Lp, scale, ctx.drop_p, ctx.seed,
-                                     L.stream()), "softmax_bwd")
-    dsp = _cols(split_planes(dpd.view(S * Lq, Lp)), Lk)
+    dsp = empty_planes(S * Lq, Lk, dev, _with_lo())              # dS only ever feeds GEMMs: planes, no fp32 copy
+    L.check(L.lib().dost_softmax_bwd_planes(L.p(prob), L.p(dpd), None, S * Lq, Lk, Lp, scale, ctx.drop_p, ctx.seed, L.p(dsp.hi),
+                                            L.p(dsp.lo), dsp.ld, L.stream()), "softmax_bwd_planes")
     # dQ = dS k
     dq = torch.empty(S, Lq, H, dtype=torch.float32, device=dev)
     gemm_planes(M=Lq, N=H, K=Lk, a=[dsp], a_mode=L.KC, b=kp, b_mode=L.MC, out=dq.view(S * Lq, H), batch=S,

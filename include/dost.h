@@ -151,6 +151,10 @@ int dost_gemm_bf16(const dost_gemm_bf16_t* g, void* workspace, size_t workspace_
 /* fp32 [rows, cols] (ld) -> bf16 planes [rows, ldp] (ldp % 8 == 0, columns >= cols zero-filled); lo may be NULL. */
 int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
                       dost_stream_t stream);
+/* Same, plus colsum[c] = sum_r x[r, c] in a fixed order (bias gradient of the Linear whose output gradient x is). */
+size_t dost_split_planes_colsum_workspace_bytes(long long rows, int cols, long long ldp);
+int dost_split_planes_colsum(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
+                             float* colsum, void* workspace, size_t workspace_bytes, dost_stream_t stream);
 
 /* fp32 row kernels of the tensor-core path (W in {128, 256, 512, 1024}): LayerNorm(+PReLU) whose output is written
  * directly as operand planes (and/or fp32), its backward (dx as fp32 and/or planes, optional residual gradient dres
@@ -239,6 +243,13 @@ int dost_softmax_fwd(int dtype, const void* s, void* p, void* pd, long long rows
                      double drop_p, unsigned long long seed, dost_stream_t stream);
 int dost_softmax_bwd(int dtype, const void* p, const void* dpd, void* ds, long long rows, int cols, long long ld, double scale,
                      double drop_p, unsigned long long seed, dost_stream_t stream);
+
+/* Same, with the (dropped-out) probabilities / the score gradients also written as bf16 hi/lo operand planes (ds may be
+ * NULL when only the planes are wanted). */
+int dost_softmax_fwd_planes(const float* s, float* p, float* pd, long long rows, int cols, long long ld, double scale,
+                            double drop_p, unsigned long long seed, void* hi, void* lo, long long ldp, dost_stream_t stream);
+int dost_softmax_bwd_planes(const float* p, const float* dpd, float* ds, long long rows, int cols, long long ld, double scale,
+                            double drop_p, unsigned long long seed, void* hi, void* lo, long long ldp, dost_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * DOS loss.  mode 0 (eDOS, main_eDOS.py:111-123): y = max(y,0); per-crystal RMSE; mean over crystals;

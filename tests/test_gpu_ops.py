@@ -743,3 +743,15 @@ def test_dense_attention_on_planes(prec, tol, S, Lq, Lk, H):
         o2, g2 = _grads(lambda: r + O.attention(q, q), [q, r])
         for a_, b_ in zip(o1 + g1, o2 + g2):
             assert relerr(a_, b_) < tol
+
+
+@pytest.mark.parametrize("rows,cols", [(1000, 256), (37, 41), (5000, 1024), (1, 8)])
+def test_split_planes_colsum(rows, cols):
+    torch.manual_seed(rows + cols)
+    x = torch.randn(rows, cols, device=DEV)
+    with ops.precision("bf16x3"):
+        pl, cs = ops.split_planes_colsum(x)
+        ref = ops.split_planes(x)
+    assert torch.equal(pl.hi, ref.hi) and torch.equal(pl.lo, ref.lo)
+    want = x.double().sum(0)
+    assert (cs.double() - want).abs().max() / want.abs().max().clamp_min(1e-6) < 1e-5
