@@ -105,6 +105,7 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
     n_layers = len(processors)
     H = x.shape[1]
     blocked = ops.tc_active(x) and ops.planes_ok(2 * H) and H % 64 == 0 and graph.E >= 128 and \
+        not os.environ.get("DOST_NO_EDGEBLOCK") and \
         (graph.by_src is not None or not torch.is_grad_enabled())
     for i, proc in enumerate(processors):
         last = i == n_layers - 1
@@ -125,7 +126,7 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
 
 def _ffn(layer, y2d):
     ln1 = layer.layer_norms[1]
-    if ops.tc_active(y2d) and ops.planes_ok(y2d.shape[1]) and y2d.shape[0] >= 128:
+    if ops.tc_active(y2d) and ops.planes_ok(y2d.shape[1]) and y2d.shape[0] >= 128 and not os.environ.get("DOST_NO_FFNBLOCK"):
         return ops.ffn_block(y2d, ln1.weight, ln1.bias, layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias)
     h = ops.layer_norm(y2d, ln1.weight, ln1.bias)
     h = ops.linear([(h, None)], layer.fc1.weight, layer.fc1.bias, act=L.ACT_RELU)
