@@ -62,6 +62,7 @@ class GemmBf16(C.Structure):
         ("split_k", C.c_int), ("precision", C.c_int),
         ("batch", C.c_int), ("a_bstride", C.c_longlong), ("b_bstride", C.c_longlong), ("c_bstride", C.c_longlong),
         ("res_bstride", C.c_longlong),
+        ("b_rowoff", C.c_void_p), ("c_rowoff", C.c_void_p), ("c_rowlim", C.c_void_p),
     ]
 
 
@@ -119,6 +120,14 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_double,
                                  C.c_double, C.c_ulonglong, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "dost_xattn_kv_ext_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_longlong, C.c_void_p]),
+    "dost_xattn_kv_ext_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]),
+    "dost_xattn_softmax_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_double,
+                                         C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "dost_xattn_softmax_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                         C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dost_softmax_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
                                    C.c_double, C.c_ulonglong, C.c_void_p]),
     "dost_softmax_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
@@ -149,7 +158,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 4:
+    if lib.dost_abi_version() != 5:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -43,6 +43,9 @@ struct Params {
   int a_mc, b_mc;
   int zmode, kchunk;            // 0: single, 1: batched (z = batch index), 2: split-K (raw partials to ws)
   long long c_bstride, res_bstride;   // batched: element strides of out / residual between batches
+  const int* b_rowoff;          // batched, ragged B: rows of problem z start at b_rowoff[z] (instead of a batch stride)
+  const int* c_rowoff;          // batched, ragged out: rows of problem z are written at c_rowoff[z] + m ...
+  const int* c_rowlim;          // ... for m < c_rowlim[z] only
   int m_tiles, n_tiles, total_tiles;
   const float* bias;
   const float* rowbias; long long ld_rowbias; int rowbias_div;
@@ -288,28 +291,32 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           const uint32_t sA = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sB = sA + (SPLIT ? 2 : 1) * A_BYTES;
           const int zb = (p.zmode == 1) ? t.z : 0;
-          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1) {
-            if (CTA2) tma_load_3d_2cta(dst, m, c0, c1, zb, bar);
-            else tma_load_3d(dst, m, c0, c1, zb, bar);
+          auto load = [&](uint32_t dst, const CUtensorMap* m, int c0, int c1, int c2) {
+            if (CTA2) tma_load_3d_2cta(dst, m, c0, c1, c2, bar);
+            else tma_load_3d(dst, m, c0, c1, c2, bar);
           };
+          // ragged B: every problem reads the same 2-D plane at its own row offset (rows past the problem's own belong
+          // to the next problem; the caller masks them)
+          const int brow = p.b_rowoff ? __ldg(p.b_rowoff + t.z) : 0;
+          const int zbb = p.b_rowoff ? 0 : zb;
           if (!a_mc) {
-            load(sA, &maps.a_hi[seg], kseg, t.m0);
-            if (SPLIT) load(sA + A_BYTES, &maps.a_lo[seg], kseg, t.m0);
+            load(sA, &maps.a_hi[seg], kseg, t.m0, zb);
+            if (SPLIT) load(sA + A_BYTES, &maps.a_lo[seg], kseg, t.m0, zb);
           } else {
 #pragma unroll
             for (int b = 0; b < BM / 64; ++b) {
-              load(sA + b * 8192, &maps.a_hi[0], t.m0 + 64 * b, k0);
-              if (SPLIT) load(sA + A_BYTES + b * 8192, &maps.a_lo[0], t.m0 + 64 * b, k0);
+              load(sA + b * 8192, &maps.a_hi[0], t.m0 + 64 * b, k0, zb);
+              if (SPLIT) load(sA + A_BYTES + b * 8192, &maps.a_lo[0], t.m0 + 64 * b, k0, zb);
             }
           }
           if (!b_mc) {
-            load(sB, CTA2 ? &maps.b_hi2 : &maps.b_hi, k0, nb0);
-            if (SPLIT) load(sB + B_BYTES, CTA2 ? &maps.b_lo2 : &maps.b_lo, k0, nb0);
+            load(sB, CTA2 ? &maps.b_hi2 : &maps.b_hi, k0, nb0 + brow, zbb);
+            if (SPLIT) load(sB + B_BYTES, CTA2 ? &maps.b_lo2 : &maps.b_lo, k0, nb0 + brow, zbb);
           } else {
 #pragma unroll
             for (int b = 0; b < BNL / 64; ++b) {
-              load(sB + b * 8192, &maps.b_hi, nb0 + 64 * b, k0);
-              if (SPLIT) load(sB + B_BYTES + b * 8192, &maps.b_lo, nb0 + 64 * b, k0);
+              load(sB + b * 8192, &maps.b_hi, nb0 + 64 * b, k0 + brow, zbb);
+              if (SPLIT) load(sB + B_BYTES + b * 8192, &maps.b_lo, nb0 + 64 * b, k0 + brow, zbb);
             }
           }
           if (++stage == NSTAGE) {
@@ -430,8 +437,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         const int n = nbase + c0;
         if (n >= p.N || t.m0 + quad * 32 >= p.M) continue;  // N % 4 == 0: a thread's 4 columns are all in or all out
         bool mok[8];
+        const int mlim = p.c_rowlim ? min(p.M, __ldg(p.c_rowlim + t.z)) : p.M;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mok[i] = mbase + 4 * i < p.M;
+        for (int i = 0; i < 8; ++i) mok[i] = mbase + 4 * i < mlim;
         if (p.zmode == 2) {
           float* ws = p.ws + ((long long)t.z * p.M + mbase) * p.N + n;
 #pragma unroll
@@ -489,7 +497,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             }
         }
         if (p.out) {
-          float* op = p.out + (p.zmode == 1 ? (long long)t.z * p.c_bstride : 0) + (long long)mbase * p.ldc + n;
+          float* op = p.out + (p.c_rowoff ? (long long)__ldg(p.c_rowoff + t.z) * p.ldc
+                                          : (p.zmode == 1 ? (long long)t.z * p.c_bstride : 0)) + (long long)mbase * p.ldc + n;
           if (p.accumulate) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
@@ -821,7 +830,17 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     DOST_REQUIRE(pl.hi && (!split3 || pl.lo), "gemm_bf16: B planes missing");
     DOST_REQUIRE(al16(pl.hi) && al16(pl.lo) && pl.ld % 8 == 0, "gemm_bf16: B planes must be 16-byte aligned, ld %% 8 == 0");
     int rc;
-    if (!b_mc) {       // [N rows, K] K-major: box {64 k, bn rows} (and {64 k, 128 rows} for CTA pairs)
+    const bool ragged_b = batch > 1 && h->b_rowoff != nullptr;   // one 2-D plane of pl.rows rows, per-problem row offsets
+    if (ragged_b) {
+      DOST_REQUIRE(pl.rows > 0, "gemm_bf16: ragged B needs the total number of stored rows");
+      if (!b_mc) {
+        rc = make_map(&maps.b_hi, pl.hi, h->K, pl.rows, pl.ld, bn);
+        if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, pl.rows, pl.ld, bn);
+      } else {
+        rc = make_map(&maps.b_hi, pl.hi, h->N, pl.rows, pl.ld, 64);
+        if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->N, pl.rows, pl.ld, 64);
+      }
+    } else if (!b_mc) {       // [N rows, K] K-major: box {64 k, bn rows} (and {64 k, 128 rows} for CTA pairs)
       const long long nrows = (pl.rows > 0 && pl.rows < h->N) ? pl.rows : h->N;   // N may be padded past the stored rows
       rc = make_map(&maps.b_hi, pl.hi, h->K, nrows, pl.ld, bn, batch, h->b_bstride);
       if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, nrows, pl.ld, bn, batch, h->b_bstride);
@@ -840,6 +859,10 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   p.zmode = split > 1 ? 2 : (batch > 1 ? 1 : 0);
   p.c_bstride = h->c_bstride;
   p.res_bstride = h->res_bstride;
+  p.b_rowoff = batch > 1 ? h->b_rowoff : nullptr;
+  p.c_rowoff = batch > 1 ? h->c_rowoff : nullptr;
+  p.c_rowlim = batch > 1 ? h->c_rowlim : nullptr;
+  DOST_REQUIRE(!p.c_rowoff || p.c_rowlim, "gemm_bf16: ragged output needs both c_rowoff and c_rowlim");
   p.kchunk = 0;
   p.ws = nullptr;
   if (split > 1) {

@@ -49,7 +49,8 @@ class DOSTransformer(nn.Module):
         K.require_cuda(self.fc.weight, "the model")
         K.require_cuda(g.x, "the batch")
         graph = ops.build_graph(g.edge_index, g.batch, g.system, nmax_override=self.max_num_nodes,
-                                need_backward=torch.is_grad_enabled())
+                                need_backward=torch.is_grad_enabled(),
+                                nmax_hint=getattr(g, "max_num_nodes", None))
         seeds = K._Seeds(self.attn_drop, self.training)
         enc = self.GN_encoder
         x = K.mlp_prelu(enc.node_encoder, g.x)

@@ -61,7 +61,8 @@ class DOSTransformer_phonon(nn.Module):
             raise NotImplementedError("radius_graph construction is a dead branch in the reference "
                                       "(DOSTransformer_phonon.py:59); provide edge_index and edge_vec")
         graph = ops.build_graph(g["edge_index"], g.batch, g.system, nmax_override=self.max_num_nodes,
-                                need_backward=torch.is_grad_enabled())
+                                need_backward=torch.is_grad_enabled(),
+                                nmax_hint=getattr(g, "max_num_nodes", None))
         seeds = K._Seeds(self.attn_drop, self.training)
         dtype = self.fc.weight.dtype
         edge_attr = ops.phonon_edge_features(g["edge_vec"].to(dtype))

@@ -150,7 +150,7 @@ def cross_stack(enc: EnergyEncoderParams, q, x_nodes, graph: ops.CrystalGraph, S
     for layer in enc.layers:
         ln0 = layer.layer_norms[0]
         kv = ops.layer_norm(x_nodes, ln0.weight, ln0.bias)
-        q_ln = ops.layer_norm(q, ln0.weight, ln0.bias)
+        q_ln = ops.layer_norm(q, ln0.weight, ln0.bias, want_planes=q.dim() == 3)
         y = ops.cross_attention(q_ln, kv, ln0.bias, q, graph, S, seeds.p, seeds.next())
         q = _ffn(layer, y.view(S * T, H)).view(S, T, H)
     return ops.layer_norm(q, enc.layer_norm.weight, enc.layer_norm.bias)

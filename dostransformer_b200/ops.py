@@ -125,11 +125,27 @@ class CrystalGraph:
     by_system: CSR       # crystals grouped by crystal system: adjoint of promt_token[g.system]
     crystals: CSR        # nodes grouped by crystal (contiguous): ptr = crystals.rowptr
     nmax: torch.Tensor   # int32 [1] on device: max nodes per crystal (to_dense_batch padding length)
+    nmax_host: Optional[int] = None   # the same number on the host when the collate / sharder knows it (no device sync)
     _trows: dict = field(default_factory=dict)
+
+    def ragged(self):
+        """(ptr_ext, n_ext): first row and row count of every crystal in the extended key plane (atoms + 1 phantom row)."""
+        if "ragged" not in self._trows:
+            ar = torch.arange(self.B, dtype=torch.int32, device=self.row.device)
+            ptr = self.crystals.rowptr
+            self._trows["ragged"] = ((ptr[:-1] + ar).contiguous(), (ptr[1:] - ptr[:-1] + 1).contiguous())
+        return self._trows["ragged"]
 
     @property
     def ptr(self) -> torch.Tensor:
         return self.crystals.rowptr
+
+    def token_mod(self, T: int) -> torch.Tensor:
+        """int32 [B*T]: t = i % T (row map that repeats a [T, H] block for every crystal)."""
+        key = ("mod", T)
+        if key not in self._trows:
+            self._trows[key] = (torch.arange(self.B * T, dtype=torch.int32, device=self.row.device) % T).contiguous()
+        return self._trows[key]
 
     def token_rowptr(self, T: int) -> torch.Tensor:
         """rowptr of the [B*T] token rows grouped by crystal (T contiguous rows each)."""
@@ -139,7 +155,7 @@ class CrystalGraph:
 
 
 def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Tensor, *, nmax_override: Optional[int] = None,
-                need_backward: bool = True) -> CrystalGraph:
+                need_backward: bool = True, nmax_hint: Optional[int] = None) -> CrystalGraph:
     """edge_index int64 [2,E] (row = centre atom, col = neighbour), batch int64 [N] sorted, system int64 [B]."""
     assert edge_index.is_cuda, "dostransformer_b200 has no CPU path: move the batch to a CUDA device"
     N, E, B = batch.numel(), edge_index.shape[1], system.numel()
@@ -155,7 +171,8 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
     crystals.perm = None
     if nmax_override is not None:     # data-parallel: global padding length fixed by the sharder
         nmax = torch.full((1,), int(nmax_override), dtype=torch.int32, device=batch.device)
-    return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax)
+    host = int(nmax_override) if nmax_override is not None else (int(nmax_hint) if nmax_hint is not None else None)
+    return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host)
 
 
 # =====================================================================================================
@@ -320,7 +337,9 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
                 dact: Optional[Planes] = None, dact_slope: float = 0.0, residual: Optional[torch.Tensor] = None,
                 accumulate: bool = False, split_k: int = 1, out_planes: Optional[Planes] = None,
                 ldc: Optional[int] = None, prec: Optional[int] = None, batch: int = 1, a_bstride: int = 0, b_bstride: int = 0,
-                c_bstride: int = 0, res_bstride: int = 0, ld_res: Optional[int] = None, b_rows: Optional[int] = None) -> None:
+                c_bstride: int = 0, res_bstride: int = 0, ld_res: Optional[int] = None, b_rows: Optional[int] = None,
+                b_rowoff: Optional[torch.Tensor] = None, c_rowoff: Optional[torch.Tensor] = None,
+                c_rowlim: Optional[torch.Tensor] = None) -> None:
     """C = epi(A B^T) on the TMA-fed tcgen05 kernel; operands are bf16 planes (see include/dost.h).
     b_rows: valid rows of a K-major B per problem when N is padded beyond them (the rest reads as zero)."""
     g = L.GemmBf16()
@@ -347,6 +366,9 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
         g.ldc = ldc if ldc is not None else _ld(out)
     g.accumulate = 1 if accumulate else 0
     g.batch, g.a_bstride, g.b_bstride, g.c_bstride, g.res_bstride = batch, a_bstride, b_bstride, c_bstride, res_bstride
+    g.b_rowoff = b_rowoff.data_ptr() if b_rowoff is not None else None
+    g.c_rowoff = c_rowoff.data_ptr() if c_rowoff is not None else None
+    g.c_rowlim = c_rowlim.data_ptr() if c_rowlim is not None else None
     if out_planes is not None:
         g.out_hi = out_planes.hi.data_ptr()
         g.out_lo = out_planes.lo.data_ptr() if out_planes.lo is not None else None
@@ -1083,7 +1105,95 @@ class _CrossAttention(torch.autograd.Function):
         return d_q, dkv, dph, d_resid, None, None, None, None
 
 
+class _CrossAttentionTC(torch.autograd.Function):
+    """The same attention with its contractions on the tensor cores: ragged batched GEMMs (one problem per sequence, the
+    keys of its crystal addressed by a row offset into one extended key plane that carries a phantom-key row per
+    crystal), fp32 softmax in between (csrc/xattn_tc.cu).  Needs S == B, no dropout and the padding length on the host."""
+
+    @staticmethod
+    def forward(ctx, q, kv, phantom, resid, graph: CrystalGraph, qpl: Optional[Planes]):
+        N, H = kv.shape
+        B = graph.B
+        T = q.shape[-2]
+        S = B
+        dev = kv.device
+        lib = L.lib()
+        npad = _pad8(graph.nmax_host + 1)
+        ptr_ext, n_ext = graph.ragged()
+        q, resid = q.contiguous(), resid.contiguous()
+        bcast_q = q.dim() == 2
+        if bcast_q:                       # first layer of the first stack: every crystal shares the energy embeddings
+            q3 = gather_rows_raw(q, graph.token_mod(T))
+            qp = split_planes(q3)
+        else:
+            qp = qpl if qpl is not None else split_planes(q.view(S * T, H))
+        kvp = empty_planes(N + B, H, dev, _with_lo())
+        L.check(lib.dost_xattn_kv_ext_build(L.p(kv), L.p(phantom), L.p(graph.batch), L.p(graph.ptr), N, B, H, L.p(kvp.hi), L.p(kvp.lo),
+                                            kvp.ld, L.stream()), "xattn_kv_ext_build")
+        scores = torch.empty(S * T, npad, dtype=torch.float32, device=dev)
+        gemm_planes(M=T, N=npad, K=H, a=[qp], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=scores, batch=S,
+                    a_bstride=T * qp.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
+        pp = empty_planes(S * T, npad, dev, _with_lo())
+        lse = torch.empty(S * T, dtype=torch.float32, device=dev)
+        scale = float(H) ** -0.5
+        L.check(lib.dost_xattn_softmax_fwd(L.p(scores), L.p(graph.ptr), L.p(graph.nmax), S * T, B, T, npad, scale, L.p(pp.hi),
+                                           L.p(pp.lo), pp.ld, L.p(lse), L.stream()), "xattn_softmax_fwd")
+        out = torch.empty(S, T, H, dtype=torch.float32, device=dev)
+        r2 = resid.view(-1, H)
+        gemm_planes(M=T, N=H, K=npad, a=[pp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=out.view(S * T, H), residual=r2,
+                    batch=S, a_bstride=T * pp.ld, c_bstride=T * H, res_bstride=(0 if resid.dim() == 2 else T * H),
+                    b_rowoff=ptr_ext)
+        ctx.save_for_backward(kv, phantom, scores, lse, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
+        ctx.graph, ctx.prec, ctx.npad = graph, _PRECISION, npad
+        ctx.bcast_q, ctx.bcast_r, ctx.T = bcast_q, resid.dim() == 2, T
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        kv, phantom, scores, lse, qh, ql, kh, kl, ph, pl_ = ctx.saved_tensors
+        g: CrystalGraph = ctx.graph
+        N, H = kv.shape
+        B, T, npad = g.B, ctx.T, ctx.npad
+        S = B
+        dev = kv.device
+        lib = L.lib()
+        with precision_value(ctx.prec):
+            ptr_ext, n_ext = g.ragged()
+            qp, kvp, pp = Planes(qh, ql, S * T, H), Planes(kh, kl, N + B, H), Planes(ph, pl_, S * T, npad)
+            d_out = d_out.contiguous()
+            dop = split_planes(d_out.view(S * T, H))
+            # dP = dO k^T
+            dP = torch.empty(S * T, npad, dtype=torch.float32, device=dev)
+            gemm_planes(M=T, N=npad, K=H, a=[dop], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=dP, batch=S,
+                        a_bstride=T * dop.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
+            dsp = empty_planes(S * T, npad, dev, _with_lo())
+            L.check(lib.dost_xattn_softmax_bwd(L.p(scores), L.p(lse), L.p(dP), L.p(g.ptr), L.p(g.nmax), S * T, B, T, npad,
+                                               float(H) ** -0.5, L.p(dsp.hi), L.p(dsp.lo), dsp.ld, L.stream()), "xattn_softmax_bwd")
+            # dQ = dS k
+            dq = torch.empty(S, T, H, dtype=torch.float32, device=dev)
+            gemm_planes(M=T, N=H, K=npad, a=[dsp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=dq.view(S * T, H), batch=S,
+                        a_bstride=T * dsp.ld, c_bstride=T * H, b_rowoff=ptr_ext)
+            # d(extended keys) = dS^T q + P^T dO, written at each crystal's rows of the extended plane
+            dext = torch.empty(N + B, H, dtype=torch.float32, device=dev)
+            gemm_planes(M=npad, N=H, K=T, a=[dsp], a_mode=L.MC, b=qp, b_mode=L.MC, out=dext, batch=S, a_bstride=T * dsp.ld,
+                        b_bstride=T * qp.ld, c_rowoff=ptr_ext, c_rowlim=n_ext)
+            gemm_planes(M=npad, N=H, K=T, a=[pp], a_mode=L.MC, b=dop, b_mode=L.MC, out=dext, accumulate=True, batch=S,
+                        a_bstride=T * pp.ld, b_bstride=T * dop.ld, c_rowoff=ptr_ext, c_rowlim=n_ext)
+            dkv = torch.empty(N, H, dtype=torch.float32, device=dev)
+            dbrows = torch.empty(B, H, dtype=torch.float32, device=dev)
+            L.check(lib.dost_xattn_kv_ext_split(L.p(dext), L.p(g.batch), L.p(g.ptr), N, B, H, L.p(dkv), L.p(dbrows), L.stream()),
+                    "xattn_kv_ext_split")
+            dph = colsum(dbrows)
+            d_q = colsum(dq.view(S, T * H)).view(T, H) if ctx.bcast_q else dq
+            d_resid = colsum(d_out.view(S, T * H)).view(T, H) if ctx.bcast_r else d_out
+        return d_q, dkv, dph, d_resid, None, None
+
+
 def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float = 0.0, seed: int = 0):
+    H = kv.shape[1]
+    if (tc_active(kv) and H % 128 == 0 and drop_p == 0.0 and S == graph.B and graph.nmax_host is not None
+            and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not os.environ.get("DOST_NO_XATTN_TC")):
+        return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q))
     return _CrossAttention.apply(q, kv, phantom, resid, graph, S, drop_p, seed)
 
 

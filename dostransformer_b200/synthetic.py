@@ -65,8 +65,11 @@ class CrystalBatch:
         return self._map(lambda t: t.pin_memory())
 
     def clone(self):
-        return CrystalBatch(**{k: (getattr(self, k).clone() if torch.is_tensor(getattr(self, k)) else
-                                   list(getattr(self, k))) for k in self._keys})
+        def cp(v):
+            if torch.is_tensor(v):
+                return v.clone()
+            return list(v) if isinstance(v, (list, tuple)) else v
+        return CrystalBatch(**{k: cp(getattr(self, k)) for k in self._keys})
 
     @property
     def num_graphs(self) -> int:
@@ -121,7 +124,10 @@ def make_edos_batch(B: int, seed: int = 2000, *, mean_atoms: float = 20.0, sigma
     return CrystalBatch(
         x=x.to(dtype), edge_index=torch.stack([row, col]), edge_attr=edge_attr.to(dtype),
         glob=glob.to(dtype), batch=batch, system=system, y_ft=y.reshape(-1).to(dtype),
-        mp_id=[f"syn-{seed}-{i}" for i in range(B)])
+        mp_id=[f"syn-{seed}-{i}" for i in range(B)],
+        # host-side collate metadata (not a reference field): the to_dense_batch padding length, known for free while the
+        # batch is assembled on the CPU; lets the model size its ragged attention tiles without a device->host read
+        max_num_nodes=int(n_nodes.max()))
 
 
 def make_large_cell_batch(B: int, seed: int = 4000, *, K: int = 24, lo: int = 200, hi: int = 400,

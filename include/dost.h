@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 4
+#define DOST_ABI_VERSION 5
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -144,6 +144,13 @@ typedef struct {
    * strides between consecutive problems of the A / B planes, of out and of residual.  Exclusive with split_k. */
   int batch;
   long long a_bstride, b_bstride, c_bstride, res_bstride;
+  /* ragged batches (variable-length atom sets of the crystals; energy->atom cross attention, DOSTransformer.py:61-63):
+   * b_rowoff[z]: B is ONE plane of b.rows rows and problem z uses rows b_rowoff[z] .. (rows past the problem's own are
+   * whatever follows in the plane: the caller masks them).  c_rowoff[z], c_rowlim[z]: rows m < c_rowlim[z] of problem z
+   * are written at row c_rowoff[z] + m of out.  All device int32 arrays of `batch` entries, or NULL. */
+  const int32_t* b_rowoff;
+  const int32_t* c_rowoff;
+  const int32_t* c_rowlim;
 } dost_gemm_bf16_t;
 
 size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g);
@@ -236,6 +243,21 @@ int dost_xattn_bwd(int dtype, const void* d_out, const void* q, long long q_sstr
                    const void* out, const void* resid, long long resid_sstride, const float* lse, void* dq,
                    void* dkv, void* dphantom, int S, int B, int T, int H, long long N, double scale, double drop_p,
                    unsigned long long seed, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* Tensor-core formulation of the same attention (fp32, no dropout, one sequence per crystal): the contractions are ragged
+ * batched dost_gemm_bf16 problems over an extended key plane [N + B, H] that holds one phantom-key row per crystal after its
+ * atoms (dost_xattn_kv_ext_build); the fp32 softmax over the n_b real columns and the phantom column (weight *nmax - n_b)
+ * writes the probabilities / score gradients as operand planes [rows, ldp] (columns past the crystal's own are zero).
+ * scores, dP: [S*T, npad] fp32; lse [S*T]; dext [N + B, H] -> dkv [N, H] and the B phantom-key rows. */
+int dost_xattn_kv_ext_build(const float* y, const float* beta, const int32_t* batch, const int32_t* ptr, long long N, int B,
+                            int H, void* hi, void* lo, long long ldp, dost_stream_t stream);
+int dost_xattn_kv_ext_split(const float* dext, const int32_t* batch, const int32_t* ptr, long long N, int B, int H, float* dkv,
+                            float* dbeta_rows, dost_stream_t stream);
+int dost_xattn_softmax_fwd(const float* scores, const int32_t* ptr, const int32_t* nmax, long long rows, int B, int T, int npad,
+                           double scale, void* hi, void* lo, long long ldp, float* lse, dost_stream_t stream);
+int dost_xattn_softmax_bwd(const float* scores, const float* lse, const float* dP, const int32_t* ptr, const int32_t* nmax,
+                           long long rows, int B, int T, int npad, double scale, void* hi, void* lo, long long ldp,
+                           dost_stream_t stream);
 
 /* Row softmax for the dense T x T self attention (layers/multihead_attention.py:68-70): p = softmax_fp32(s*scale);
  * pd = dropout(p); rows are ld elements apart (ld >= cols).  Backward: ds = scale * p * (dp - sum(dp*p)) with dp = mask/(1-p) * dpd. */

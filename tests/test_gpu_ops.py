@@ -755,3 +755,39 @@ def test_split_planes_colsum(rows, cols):
     assert torch.equal(pl.hi, ref.hi) and torch.equal(pl.lo, ref.lo)
     want = x.double().sum(0)
     assert (cs.double() - want).abs().max() / want.abs().max().clamp_min(1e-6) < 1e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("H,broadcast,T,sizes", [(128, False, 201, None), (256, True, 201, None), (128, False, 70, [150, 40, 301, 7])])
+def test_cross_attention_tensor_core_formulation(prec, tol, H, broadcast, T, sizes):
+    """Ragged batched GEMMs + phantom-key column (ops._CrossAttentionTC) against the padded dense reference."""
+    from dostransformer_b200.synthetic import make_edos_batch
+    if sizes is None:
+        g = make_edos_batch(6, seed=31, mean_atoms=9.0, max_atoms=50)
+    else:
+        g = make_edos_batch(len(sizes), seed=31, sizes=torch.tensor(sizes))
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV), nmax_hint=g.max_num_nodes)
+    B = gr.B
+    xn = _leaf(_rand(gr.N, H, dtype=torch.float32, seed=1))
+    q = _leaf(_rand(T, H, dtype=torch.float32, seed=2)) if broadcast else _leaf(_rand(B, T, H, dtype=torch.float32, seed=2))
+    gam, bet = _leaf(_rand(H, dtype=torch.float32, seed=3)), _leaf(_rand(H, dtype=torch.float32, seed=4))
+    bd = g.batch.to(DEV)
+
+    def mine():
+        with ops.precision(prec):
+            kv = ops.layer_norm(xn, gam, bet)
+            ql = ops.layer_norm(q, gam, bet, want_planes=q.dim() == 3)
+            assert ops.tc_active(kv)
+            out = ops.cross_attention(ql, kv, bet, q, gr, B)
+            assert type(out.grad_fn).__name__.startswith("_CrossAttentionTC")
+            return out
+
+    def ref():
+        qq = q[None].expand(B, T, H) if broadcast else q
+        return _dense_cross_ref(qq, xn, gam, bet, bd, H)
+
+    with ops.precision(prec):
+        o1, g1 = _grads(mine, [xn, q, gam, bet])
+    o2, g2 = _grads(ref, [xn, q, gam, bet])
+    for name, a_, b_ in zip(["out", "dx", "dq", "dgamma", "dbeta"], o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol, (name, relerr(a_, b_))
