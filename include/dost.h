@@ -284,6 +284,16 @@ int dost_loss_bwd(int dtype, int mode, const void* pred_g, const void* pred_s, c
                   int T, const void* saved, const void* grad_loss, void* d_pred_g, void* d_pred_s,
                   dost_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused multi-tensor AdamW, fp32 (torch.optim.AdamW(lr, weight_decay=1e-2), main_eDOS.py:93,127 / main_phDOS.py:90):
+ * the step right after the hot path.  Host arrays of `ntensors` device pointers / element counts;
+ * `step` is the 1-based step count used for the bias corrections.  Tensors without a gradient are simply not listed
+ * (torch skips grad-is-None parameters, which keeps the reference's dead parameters at their initial values).
+ * ------------------------------------------------------------------------------------------- */
+int dost_adamw_step(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg,
+                    void* const* exp_avg_sq, const long long* numel, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, long long step, dost_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

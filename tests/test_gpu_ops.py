@@ -791,3 +791,25 @@ def test_cross_attention_tensor_core_formulation(prec, tol, H, broadcast, T, siz
     o2, g2 = _grads(ref, [xn, q, gam, bet])
     for name, a_, b_ in zip(["out", "dx", "dq", "dgamma", "dbeta"], o1 + g1, o2 + g2):
         assert relerr(a_, b_) < tol, (name, relerr(a_, b_))
+
+
+def test_fused_adamw_matches_torch():
+    """dost_adamw_step against torch.optim.AdamW over several steps, with a parameter that never gets a gradient."""
+    from dostransformer_b200.optim import AdamW
+    torch.manual_seed(0)
+    shapes = [(1024, 256), (256,), (1,), (777, 33), (512, 768), (4097,)] + [(64, 64)] * 40
+    ref_p = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes] + [torch.nn.Parameter(torch.ones(5, device=DEV))]
+    my_p = [torch.nn.Parameter(p.detach().clone()) for p in ref_p]
+    ref = torch.optim.AdamW(ref_p, lr=1e-3, weight_decay=1e-2)
+    mine = AdamW(my_p, lr=1e-3, weight_decay=1e-2)
+    for it in range(5):
+        for a, b in zip(ref_p[:-1], my_p[:-1]):
+            g = torch.randn_like(a) * (10.0 ** (it - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        ref.step()
+        mine.step()
+    for a, b in zip(ref_p, my_p):
+        assert relerr(b, a) < 2e-6
+    assert torch.equal(my_p[-1].detach(), torch.ones(5, device=DEV))      # grad is None: untouched, like torch
+    sd = mine.state_dict()
+    assert sd["state"][0]["exp_avg"].shape == (1024, 256) and int(sd["state"][0]["step"]) == 5
