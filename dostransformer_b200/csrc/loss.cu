@@ -134,3 +134,82 @@ extern "C" int dost_loss_bwd(int dtype, int mode, const void* pred_g, const void
   }
   return check_launch("loss_bwd");
 }
+
+// ------------------------------------------------------------------------------------------------ evaluation metrics
+// utils.test (utils.py:61-112) evaluates with batch_size = 1: per crystal, targets and predictions clamped at 0, then
+// MSE, RMSE, MAE and R^2 = 1 - SSE / sum (y - mean y)^2 over its T energies; the epoch numbers are the means over the
+// crystals.  One block per crystal writes (mse, rmse, mae, r2); dost_eval_metrics reduces them in a fixed order.
+namespace dost {
+
+template <typename T>
+__global__ void __launch_bounds__(128) eval_crystal_kernel(const T* __restrict__ pred, const T* __restrict__ y, int clamp_pred, int Tn,
+                                                           T* __restrict__ per) {
+  __shared__ T red[4][4];
+  const int b = blockIdx.x;
+  const T* p = pred + (long long)b * Tn;
+  const T* yy = y + (long long)b * Tn;
+  T sse = T(0), sae = T(0), sy = T(0), sy2 = T(0);
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+    T yt = yy[t], pt = p[t];
+    if (yt < T(0)) yt = T(0);
+    if (clamp_pred && pt < T(0)) pt = T(0);
+    const T d = yt - pt;
+    sse = fma(d, d, sse);
+    sae += (d < T(0) ? -d : d);
+    sy += yt;
+    sy2 = fma(yt, yt, sy2);
+  }
+  sse = warp_sum(sse); sae = warp_sum(sae); sy = warp_sum(sy); sy2 = warp_sum(sy2);
+  if ((threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    red[0][w] = sse; red[1][w] = sae; red[2][w] = sy; red[3][w] = sy2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T v[4];
+    for (int k = 0; k < 4; ++k) v[k] = (red[k][0] + red[k][1]) + (red[k][2] + red[k][3]);
+    const T mse = v[0] / T(Tn);
+    const T sst = v[3] - v[2] * v[2] / T(Tn);
+    per[4 * b + 0] = mse;
+    per[4 * b + 1] = sqrt(mse);
+    per[4 * b + 2] = v[1] / T(Tn);
+    per[4 * b + 3] = T(1) - v[0] / sst;      // sklearn.metrics.r2_score of the flattened crystal (utils.py:20-23)
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) eval_mean_kernel(const T* __restrict__ per, int B, T* __restrict__ out) {
+  __shared__ double red[4][256];
+  for (int k = 0; k < 4; ++k) {
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) acc += (double)per[4 * b + k];
+    red[k][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int i = 0; i < 256; ++i) s += red[threadIdx.x][i];
+    out[threadIdx.x] = (T)(s / B);
+  }
+}
+
+template <typename T>
+static int run_eval(const void* pred, const void* y, int clamp_pred, int B, int Tn, void* per, void* mean, cudaStream_t st) {
+  eval_crystal_kernel<T><<<B, 128, 0, st>>>((const T*)pred, (const T*)y, clamp_pred, Tn, (T*)per);
+  int rc = check_launch("eval_metrics per crystal");
+  if (rc != DOST_OK || !mean) return rc;
+  eval_mean_kernel<T><<<1, 256, 0, st>>>((const T*)per, B, (T*)mean);
+  return check_launch("eval_metrics mean");
+}
+
+}  // namespace dost
+
+extern "C" int dost_eval_metrics(int dtype, const void* pred, const void* y, int clamp_pred, int B, int T, void* per_crystal, void* mean,
+                                 dost_stream_t stream) {
+  DOST_REQUIRE(pred && y && per_crystal && B > 0 && T > 0, "eval_metrics: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == DOST_F32) return dost::run_eval<float>(pred, y, clamp_pred, B, T, per_crystal, mean, st);
+  if (dtype == DOST_F64) return dost::run_eval<double>(pred, y, clamp_pred, B, T, per_crystal, mean, st);
+  dost::set_error("eval_metrics: unsupported dtype %d", dtype);
+  return DOST_ERR_UNSUPPORTED;
+}

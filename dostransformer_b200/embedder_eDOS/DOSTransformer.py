@@ -39,6 +39,7 @@ class DOSTransformer(nn.Module):
         self.fc_prompt = nn.Linear(2 * h + h // 2, h)
         self.fc = nn.Linear(2 * h, h)
         self.device = device
+        self.per_crystal_eval = False  # eval(): treat every crystal as its own batch (reference eval loaders use batch_size 1)
         self.max_num_nodes = None      # data-parallel: global padding length (phantom-key count) set by the sharder
 
     def forward(self, g):
@@ -50,7 +51,8 @@ class DOSTransformer(nn.Module):
         K.require_cuda(g.x, "the batch")
         graph = ops.build_graph(g.edge_index, g.batch, g.system, nmax_override=self.max_num_nodes,
                                 need_backward=torch.is_grad_enabled(),
-                                nmax_hint=getattr(g, "max_num_nodes", None))
+                                nmax_hint=getattr(g, "max_num_nodes", None),
+                                phantoms=not (self.per_crystal_eval and not self.training))
         seeds = K._Seeds(self.attn_drop, self.training)
         enc = self.GN_encoder
         x = K.mlp_prelu(enc.node_encoder, g.x)

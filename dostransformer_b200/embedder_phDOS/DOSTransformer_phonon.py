@@ -48,6 +48,7 @@ class DOSTransformer_phonon(nn.Module):
         self.fc = nn.Linear(2 * h, h)
         self.fc_prompt = nn.Linear(2 * h + h // 2, h)
         self.device = device
+        self.per_crystal_eval = False  # eval(): treat every crystal as its own batch (reference eval loaders use batch_size 1)
         self.max_num_nodes = None
 
     def forward(self, g):
@@ -62,7 +63,8 @@ class DOSTransformer_phonon(nn.Module):
                                       "(DOSTransformer_phonon.py:59); provide edge_index and edge_vec")
         graph = ops.build_graph(g["edge_index"], g.batch, g.system, nmax_override=self.max_num_nodes,
                                 need_backward=torch.is_grad_enabled(),
-                                nmax_hint=getattr(g, "max_num_nodes", None))
+                                nmax_hint=getattr(g, "max_num_nodes", None),
+                                phantoms=not (self.per_crystal_eval and not self.training))
         seeds = K._Seeds(self.attn_drop, self.training)
         dtype = self.fc.weight.dtype
         edge_attr = ops.phonon_edge_features(g["edge_vec"].to(dtype))

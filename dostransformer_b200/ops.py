@@ -155,7 +155,7 @@ class CrystalGraph:
 
 
 def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Tensor, *, nmax_override: Optional[int] = None,
-                need_backward: bool = True, nmax_hint: Optional[int] = None) -> CrystalGraph:
+                need_backward: bool = True, nmax_hint: Optional[int] = None, phantoms: bool = True) -> CrystalGraph:
     """edge_index int64 [2,E] (row = centre atom, col = neighbour), batch int64 [N] sorted, system int64 [B]."""
     assert edge_index.is_cuda, "dostransformer_b200 has no CPU path: move the batch to a CUDA device"
     N, E, B = batch.numel(), edge_index.shape[1], system.numel()
@@ -172,6 +172,8 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
     if nmax_override is not None:     # data-parallel: global padding length fixed by the sharder
         nmax = torch.full((1,), int(nmax_override), dtype=torch.int32, device=batch.device)
     host = int(nmax_override) if nmax_override is not None else (int(nmax_hint) if nmax_hint is not None else None)
+    if not phantoms:      # per-crystal evaluation (the reference's batch_size-1 loaders): no padding, hence no phantom keys
+        nmax = torch.zeros(1, dtype=torch.int32, device=batch.device)
     return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host)
 
 
@@ -1358,6 +1360,18 @@ class _DosLoss(torch.autograd.Function):
 def dos_loss(pred_global, pred_system, target, *, mode: str = "edos", beta: float = 1.0):
     """mode 'edos': main_eDOS.py:111-123 (targets clamped at 0, per-crystal RMSE); 'phonon': main_phDOS.py:109-114."""
     return _DosLoss.apply(pred_global, pred_system, target, 0 if mode == "edos" else 1, float(beta))
+
+
+def eval_metrics(pred: torch.Tensor, target: torch.Tensor, clamp_pred: bool = True):
+    """(per_crystal [B,4] = mse, rmse, mae, r2; mean [4]) as utils.test computes them with batch_size 1 (utils.py:74-88)."""
+    B, T = pred.shape
+    pred = pred.contiguous()
+    target = target.reshape(B, T).contiguous()
+    per = torch.empty(B, 4, dtype=pred.dtype, device=pred.device)
+    mean = torch.empty(4, dtype=pred.dtype, device=pred.device)
+    L.check(L.lib().dost_eval_metrics(L.dt(pred), L.p(pred), L.p(target), 1 if clamp_pred else 0, B, T, L.p(per), L.p(mean),
+                                      L.stream()), "eval_metrics")
+    return per, mean
 
 
 def phonon_edge_features(edge_vec: torch.Tensor) -> torch.Tensor:

@@ -284,6 +284,12 @@ int dost_loss_bwd(int dtype, int mode, const void* pred_g, const void* pred_s, c
                   int T, const void* saved, const void* grad_loss, void* d_pred_g, void* d_pred_s,
                   dost_stream_t stream);
 
+/* Evaluation metrics of utils.test / utils.test_phonon (utils.py:61-143), on the device: per crystal (the reference
+ * evaluates with batch_size 1) targets clamped at 0 (and predictions if clamp_pred: eDOS, utils.py:74-76),
+ * per_crystal [B,4] = (mse, rmse, mae, r2 = 1 - SSE / sum (y - mean y)^2); mean [4] (optional) = their means over crystals. */
+int dost_eval_metrics(int dtype, const void* pred, const void* y, int clamp_pred, int B, int T, void* per_crystal, void* mean,
+                      dost_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused multi-tensor AdamW, fp32 (torch.optim.AdamW(lr, weight_decay=1e-2), main_eDOS.py:93,127 / main_phDOS.py:90):
  * the step right after the hot path.  Host arrays of `ntensors` device pointers / element counts;

@@ -256,3 +256,43 @@ def test_large_cell_against_oracle(prec):
     # FMA path and every other tensor stay within the usual floors).  Stated bound for such ill-conditioned reductions:
     floor = GRAD_FLOOR[prec] if prec == "fp32" else (2e-2, 1e-1)
     _check_grads(grads, rgrads32, rgrads, floor=floor)
+
+
+def test_evaluate_matches_reference_eval_loop():
+    """utils.test (utils.py:61-112) with batch_size 1 via the oracle, against one batched per-crystal sweep on the GPU."""
+    from dostransformer_b200.evaluate import evaluate
+    torch.manual_seed(3)
+    m = DOSTransformer(2, 1, 200, 41, 2, 128, torch.device(DEV), 0.0)
+    sd = {k: v.cpu() for k, v in O.state_dict_of(m).items()}
+    singles = [make_edos_batch(1, seed=900 + i, mean_atoms=12.0) for i in range(6)]
+    rm, ms, ma, r2 = [], [], [], []
+    for g1 in singles:                                   # the reference's loop, one crystal per batch
+        dg, x, ds = O.edos_forward(sd, g1)
+        y = g1.y_ft.clamp_min(0).reshape(1, -1)
+        p = ds.clamp_min(0)
+        mse = ((y - p) ** 2).mean(dim=1)
+        ms.append(mse.mean()); rm.append(mse.sqrt().mean()); ma.append((p - y).abs().mean())
+        r2.append(1 - ((y - p) ** 2).sum() / ((y - y.mean()) ** 2).sum())
+    want = [torch.stack(v).mean().item() for v in (rm, ms, ma, r2)]
+    # the same six crystals in two batches of three
+    from dostransformer_b200.dp import take_crystals
+    big = _concat(singles)
+    m.to(DEV)
+    got = evaluate(m, [take_crystals(big, [0, 1, 2]).to(DEV), take_crystals(big, [3, 4, 5]).to(DEV)])
+    for a, b in zip(got[:4], want):
+        assert abs(a - b) < 2e-4 * max(abs(b), 1e-3), (got[:4], want)
+    ids, preds, y, emb = got[4][0]
+    assert preds.shape == (6, 201) and y.shape == (6, 201) and emb.shape == (6, 128) and len(ids) == 6
+    assert m.per_crystal_eval is False
+
+
+def _concat(gs):
+    """PyG-style collate of single-crystal batches (node offsets added to edge_index)."""
+    off, xs, eis, eas, bs = 0, [], [], [], []
+    for i, g in enumerate(gs):
+        xs.append(g.x); eis.append(g.edge_index + off); eas.append(g.edge_attr)
+        bs.append(torch.full((g.x.shape[0],), i, dtype=torch.long))
+        off += g.x.shape[0]
+    return CrystalBatch(x=torch.cat(xs), edge_index=torch.cat(eis, 1), edge_attr=torch.cat(eas), glob=torch.cat([g.glob for g in gs]),
+                        batch=torch.cat(bs), system=torch.cat([g.system for g in gs]), y_ft=torch.cat([g.y_ft for g in gs]),
+                        mp_id=sum([g.mp_id for g in gs], []), max_num_nodes=max(g.max_num_nodes for g in gs))
