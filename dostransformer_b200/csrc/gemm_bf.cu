@@ -771,7 +771,7 @@ static bool use_cta_pairs(int M, int N) {
     const char* e = getenv("DOST_GEMM_2CTA");
     return (e && e[0] == '0') ? 0 : 1;
   }();
-  return enabled && M >= 256 && N > 128;
+  return enabled && M > 128 && N > 128;
 }
 
 static inline bool al16(const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; }
@@ -836,6 +836,8 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
       if (!b_mc) {
         rc = make_map(&maps.b_hi, pl.hi, h->K, pl.rows, pl.ld, bn);
         if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->K, pl.rows, pl.ld, bn);
+        if (rc == DOST_OK && pairs) rc = make_map(&maps.b_hi2, pl.hi, h->K, pl.rows, pl.ld, 128);
+        if (rc == DOST_OK && pairs && split3) rc = make_map(&maps.b_lo2, pl.lo, h->K, pl.rows, pl.ld, 128);
       } else {
         rc = make_map(&maps.b_hi, pl.hi, h->N, pl.rows, pl.ld, 64);
         if (rc == DOST_OK && split3) rc = make_map(&maps.b_lo, pl.lo, h->N, pl.rows, pl.ld, 64);
