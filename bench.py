@@ -250,8 +250,8 @@ def kernel_rooflines(B: int, pk, precision: str):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures of the fc2-forward
-# GEMM (profiles/r1_ncu_gemm_bf_*.summary.txt); algorithmic bytes of that launch: 421 MB planes + 105 MB output.
-NCU_TRAFFIC = {"bf16x3": 511.0e6, "bf16": None, "fp32": None}
+# GEMM (profiles/r1_ncu_gemm_bf_pairs_fc2_x3.summary.txt); algorithmic bytes of that launch: 421 MB planes + 105 MB output.
+NCU_TRAFFIC = {"bf16x3": 507.4e6, "bf16": None, "fp32": None}
 
 
 def run_product(args, rank: int, world: int, local_rank: int):
