@@ -271,7 +271,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
     pk = peaks()
     B = args.batch
     NB = 3
-    host = [b.pin_memory() for b in make_batches(rank, NB, B)]
+    host = [b.pin_memory() for b in make_batches(rank if args.data_rank < 0 else args.data_rank, NB, B)]
     nmax = max(int(torch.bincount(b.batch).max()) for b in host)
     n_nodes = sum(b.batch.numel() for b in host) / NB
     n_edges = sum(b.edge_index.shape[1] for b in host) / NB
@@ -279,10 +279,12 @@ def run_product(args, rank: int, world: int, local_rank: int):
         t = torch.tensor([nmax], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         nmax = int(t.item())
+    if args.nmax > 0:
+        nmax = max(nmax, args.nmax)
     torch.manual_seed(0)
     model = DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, dev, 0.0, precision=args.precision).to(dev).train()
     model.max_num_nodes = nmax            # global padding length: the only cross-rank coupling besides the grads
-    reducer = GradReducer(live_named_parameters(model)) if world > 1 else None
+    reducer = GradReducer(live_named_parameters(model)) if (world > 1 and not os.environ.get("DOST_BENCH_NO_REDUCER")) else None
     weight = 1.0 / world
     resident = [b.clone().to(dev) for b in host]
 
@@ -451,6 +453,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed CPU baseline steps (bounded sample, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra bf16-mode measurement")
+    ap.add_argument("--nmax", type=int, default=0, help="(experiments) force a larger global padding length")
+    ap.add_argument("--data-rank", type=int, default=-1, help="(experiments) generate the batches of another rank")
     ap.add_argument("--precision", default=os.environ.get("DOST_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="GEMM path: fp32 FMA pipe | tcgen05 bf16x3 (fp32 parity, default) | tcgen05 bf16")
     args = ap.parse_args()

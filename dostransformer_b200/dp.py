@@ -200,8 +200,8 @@ class GradReducer:
                     work.wait()
                     if self.average:
                         flat.div_(world)
-                    for p, red in zip(b, torch._utils._unflatten_dense_tensors(flat, [p.grad for p in b])):
-                        p.grad.copy_(red)
+                    gl = [p.grad for p in b]
+                    torch._foreach_copy_(gl, list(torch._utils._unflatten_dense_tensors(flat, gl)))   # one launch per bucket
             else:
                 work.wait()
                 if self.average:
