@@ -125,3 +125,19 @@ def test_ops_raise_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_fused_adamw_interface_mirrors_torch():
+    """Constructor defaults, param_groups and the state_dict layout of torch.optim.AdamW (no device work)."""
+    from dostransformer_b200.optim import AdamW
+    ps = [torch.nn.Parameter(torch.zeros(3, 2)), torch.nn.Parameter(torch.zeros(5))]
+    opt = AdamW(ps, lr=1e-4, weight_decay=1e-2)
+    ref = torch.optim.AdamW(ps, lr=1e-4, weight_decay=1e-2)
+    for k in ("lr", "betas", "eps", "weight_decay"):
+        assert opt.param_groups[0][k] == ref.param_groups[0][k]
+    opt.step()                                  # nothing has a gradient: a no-op, like torch
+    sd = opt.state_dict()
+    assert sd["state"] == {} and sd["param_groups"][0]["params"] == [0, 1]
+    opt.zero_grad()
+    with pytest.raises(ValueError):
+        AdamW([])
