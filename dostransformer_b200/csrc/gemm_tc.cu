@@ -6,7 +6,7 @@
 // Precision modes
 //   bf16x3 (NSPLIT = 3): x = hi + lo with hi = bf16(x), lo = bf16(x - hi); the product is accumulated as
 //                        hi*hi + hi*lo + lo*hi (three tcgen05.mma per k-step into the same TMEM accumulator).
-//                        Relative error per product ~2^-16: this is the fp32-parity path.
+//                        Relative error per product ~2^-16.
 //   bf16   (NSPLIT = 1): operands rounded to bf16 once.
 //
 // Structure (one CTA per SM, persistent over output tiles, 416 threads):
@@ -17,8 +17,10 @@
 //                          UMMA canonical SWIZZLE_128B layout (K-major when the reduction index is contiguous in
 //                          HBM, MN-major otherwise: no transposition in either case) -> fence.proxy.async -> mbarrier
 // Pipelines: smem full/empty ring (producers <-> MMA), double-buffered TMEM accumulator full/empty (MMA <-> epilogue).
-// Activations are fp32 in HBM, so TMA (which cannot convert) is not used for the operands; the conversion is what the
-// producer warps are for.
+// The operands of this kernel are fp32 in HBM, so TMA (which cannot convert) is not used; the conversion is what the
+// producer warps are for, and it is what bounds the kernel (L1TEX wavefronts of the LDG/STS traffic, ~0.2 PFLOP/s).
+// Every large GEMM of the model therefore runs on gemm_bf.cu (operands pre-split into bf16 planes by their producers,
+// pure TMA -> tcgen05); this kernel remains for operands with row maps (gathers, broadcasts) and odd widths.
 #include <cuda_bf16.h>
 #include "gemm_common.cuh"
 
@@ -123,21 +125,6 @@ __device__ __forceinline__ void convert4(const float4& x, uint2& hi, uint2& lo) 
     lo.x = pack_bf16(x.x - __uint_as_float(hi.x << 16), x.y - __uint_as_float(hi.x & 0xFFFF0000u));
     lo.y = pack_bf16(x.z - __uint_as_float(hi.y << 16), x.w - __uint_as_float(hi.y & 0xFFFF0000u));
   }
-}
-
-// 4 consecutive fp32 starting at p (nullptr -> zeros).  `fast` (uniform over the CTA for one operand and k-tile) says
-// that every in-range item is 16-byte aligned and has all 4 elements in range.
-__device__ __forceinline__ float4 fetch4(const float* p, int nvalid, bool fast) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (fast) {
-    if (p != nullptr) v = __ldg(reinterpret_cast<const float4*>(p));
-  } else if (p != nullptr) {
-    if (nvalid > 0) v.x = __ldg(p);
-    if (nvalid > 1) v.y = __ldg(p + 1);
-    if (nvalid > 2) v.z = __ldg(p + 2);
-    if (nvalid > 3) v.w = __ldg(p + 3);
-  }
-  return v;
 }
 
 __device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
