@@ -63,6 +63,7 @@ class GemmBf16(C.Structure):
         ("batch", C.c_int), ("a_bstride", C.c_longlong), ("b_bstride", C.c_longlong), ("c_bstride", C.c_longlong),
         ("res_bstride", C.c_longlong),
         ("b_rowoff", C.c_void_p), ("c_rowoff", C.c_void_p), ("c_rowlim", C.c_void_p),
+        ("colsum", C.c_void_p),
     ]
 
 
@@ -161,7 +162,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 5:
+    if lib.dost_abi_version() != 6:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib

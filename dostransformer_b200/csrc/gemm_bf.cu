@@ -56,6 +56,7 @@ struct Params {
   float* out; long long ldc; int accumulate;
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_op;
   float* ws;
+  float* colpart;               // [ceil(M / 32)][N] per-32-row column sums of the stored value (bias gradients)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -529,6 +530,22 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
               }
             }
         }
+        if (p.colpart) {       // column sums of this warp's 32 rows, fixed order: the thread's 8 rows, then xor-8, xor-16
+          float cs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (mok[i]) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) cs[j] += v[i][j];
+            }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+            cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+          }
+          if (lane < 8)
+            *reinterpret_cast<float4*>(p.colpart + (long long)((t.m0 + quad * 32) >> 5) * p.N + n) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+        }
       }
     }
   }
@@ -895,6 +912,17 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   p.residual = h->residual; p.ld_res = h->ld_res;
   p.out = h->out; p.ldc = h->ldc; p.accumulate = h->accumulate;
   p.out_hi = (__nv_bfloat16*)h->out_hi; p.out_lo = (__nv_bfloat16*)h->out_lo; p.ld_op = h->ld_op;
+  p.colpart = nullptr;
+  const int nrb = (h->M + 31) / 32;
+  if (h->colsum) {
+    DOST_REQUIRE(split == 1 && batch == 1, "gemm_bf16: colsum needs a plain (single, un-split) problem");
+    const size_t need = sizeof(float) * (size_t)nrb * h->N;
+    if (!workspace || workspace_bytes < need) {
+      set_error("gemm_bf16: colsum workspace too small (%zu < %zu)", workspace_bytes, need);
+      return DOST_ERR_WORKSPACE;
+    }
+    p.colpart = (float*)workspace;
+  }
   DOST_REQUIRE(h->out || h->out_hi, "gemm_bf16: no output");
   DOST_REQUIRE(!h->out || (al16(h->out) && h->ldc % 4 == 0), "gemm_bf16: out must be 16-byte aligned with ldc %% 4 == 0");
   DOST_REQUIRE(!h->bias || al16(h->bias), "gemm_bf16: bias must be 16-byte aligned");
@@ -916,6 +944,11 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
                   : (bn == 128 ? launch<1, 128, false>(maps, p, st) : launch<1, 256, false>(maps, p, st));
   }
   if (rc != DOST_OK) return rc;
+  if (h->colsum) {
+    colsum_stage2_kernel<<<ceil_div(h->N, 32), 256, 0, st>>>(p.colpart, nrb, h->N, h->colsum);
+    rc = check_launch("gemm_bf16 column sums");
+    if (rc != DOST_OK) return rc;
+  }
   if (split > 1) {
     const long long total4 = (long long)h->M * h->N / 4;
     int blocks = (int)min64((total4 + 255) / 256, (long long)kNumSMs * 8);
@@ -930,7 +963,9 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
 }  // namespace dost
 
 extern "C" size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g) {
-  if (!g || g->split_k <= 1) return 0;
+  if (!g) return 0;
+  if (g->colsum) return sizeof(float) * (size_t)((g->M + 31) / 32) * g->N;
+  if (g->split_k <= 1) return 0;
   return sizeof(float) * (size_t)g->split_k * g->M * g->N;
 }
 

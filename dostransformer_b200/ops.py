@@ -341,7 +341,7 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
                 ldc: Optional[int] = None, prec: Optional[int] = None, batch: int = 1, a_bstride: int = 0, b_bstride: int = 0,
                 c_bstride: int = 0, res_bstride: int = 0, ld_res: Optional[int] = None, b_rows: Optional[int] = None,
                 b_rowoff: Optional[torch.Tensor] = None, c_rowoff: Optional[torch.Tensor] = None,
-                c_rowlim: Optional[torch.Tensor] = None) -> None:
+                c_rowlim: Optional[torch.Tensor] = None, colsum_out: Optional[torch.Tensor] = None) -> None:
     """C = epi(A B^T) on the TMA-fed tcgen05 kernel; operands are bf16 planes (see include/dost.h).
     b_rows: valid rows of a K-major B per problem when N is padded beyond them (the rest reads as zero)."""
     g = L.GemmBf16()
@@ -377,9 +377,10 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
         g.ld_op = out_planes.ld
     g.split_k = split_k
     g.precision = _PRECISION if prec is None else prec
+    g.colsum = colsum_out.data_ptr() if colsum_out is not None else None
     lib = L.lib()
     ws, nb = None, 0
-    if split_k > 1:
+    if split_k > 1 or colsum_out is not None:
         nb = lib.dost_gemm_bf16_workspace_bytes(C.byref(g))
         ws = _ws(nb, b.hi.device)
     L.check(lib.dost_gemm_bf16(C.byref(g), L.p(ws), nb, L.stream()), "gemm_bf16")
@@ -503,8 +504,9 @@ class _FFNBlock(torch.autograd.Function):
             gemm_planes(M=H, N=F, K=M, a=[dop], a_mode=L.MC, b=h1p, b_mode=L.MC, out=dw2, split_k=_split_for(H, F, M))
             # d(relu input) = (d_out W2) * relu'(h1): relu' from the sign of the saved hi plane, result as planes only
             dv1p = empty_planes(M, F, dev, _with_lo())
-            gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p, dact_slope=0.0, out_planes=dv1p)
-            db1 = colsum_planes(dv1p)
+            db1 = torch.empty(F, dtype=torch.float32, device=dev)      # bias gradient from the epilogue that writes dv1
+            gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p, dact_slope=0.0, out_planes=dv1p,
+                        colsum_out=db1)
             dw1 = torch.empty(F, H, dtype=torch.float32, device=dev)
             gemm_planes(M=F, N=H, K=M, a=[dv1p], a_mode=L.MC, b=h0p, b_mode=L.MC, out=dw1, split_k=_split_for(F, H, M))
             dh0 = torch.empty(M, H, dtype=torch.float32, device=dev)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 5
+#define DOST_ABI_VERSION 6
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -151,6 +151,9 @@ typedef struct {
   const int32_t* b_rowoff;
   const int32_t* c_rowoff;
   const int32_t* c_rowlim;
+  /* optional: colsum[n] = sum_m (stored value)[m, n] in a fixed order, computed by the epilogue that stores it (the bias
+   * gradient when the stored value is the gradient of a Linear's output); workspace ceil(M/32)*N floats; no split_k/batch */
+  float* colsum;
 } dost_gemm_bf16_t;
 
 size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g);
