@@ -93,6 +93,10 @@ _SIGNATURES = {
                                      C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),
+    "dost_rowdot_fwd": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p]),
+    "dost_rowdot_bwd_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
+    "dost_rowdot_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "dost_colsum_planes_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int]),
     "dost_colsum_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
                                      C.c_size_t, C.c_void_p]),

@@ -307,6 +307,76 @@ __global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------- Linear(H -> 1)
+// out_layer (DOSTransformer.py:75,89): one dot product per energy token.  A 128 x 128 GEMM tile would be 127/128 padding;
+// these are streaming kernels (one warp per row, 16-byte loads): forward reads x once, backward reads x once and writes dx.
+template <int NV>   // K = 128 * NV
+__global__ void __launch_bounds__(kWarps * 32) rowdot_fwd_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ out, long long M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wv[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+  const float b = bias ? __ldg(bias) : 0.f;
+  for (long long r = blockIdx.x * (long long)kWarps + warp; r < M; r += (long long)gridDim.x * kWarps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + lane + 32 * i);
+      s += (v.x * wv[i].x + v.y * wv[i].y) + (v.z * wv[i].z + v.w * wv[i].w);
+    }
+    s = warp_sum(s);
+    if (lane == 0) out[r] = s + b;
+  }
+}
+
+// dx[m, :] = dout[m] w;  ws[block][0..K) = partial dw = sum_m dout[m] x[m, :],  ws[block][K] = partial db = sum_m dout[m]
+template <int NV>
+__global__ void __launch_bounds__(kWarps * 32) rowdot_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ x,
+                                                                 long long ldx, const float* __restrict__ w, float* __restrict__ dx,
+                                                                 float* __restrict__ ws, long long M, long long rows_per_block) {
+  constexpr int K = 128 * NV;
+  __shared__ __align__(16) float sm[kWarps][K];
+  __shared__ float sb[kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 wv[NV], acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    wv[i] = __ldg(reinterpret_cast<const float4*>(w) + lane + 32 * i);
+    acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float bsum = 0.f;
+  const long long rbeg = blockIdx.x * rows_per_block, rend = min(M, rbeg + rows_per_block);
+  for (long long r = rbeg + warp; r < rend; r += kWarps) {
+    const float g = __ldg(dout + r);
+    bsum += g;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * ldx) + lane + 32 * i);
+      acc[i].x = fmaf(g, v.x, acc[i].x); acc[i].y = fmaf(g, v.y, acc[i].y);
+      acc[i].z = fmaf(g, v.z, acc[i].z); acc[i].w = fmaf(g, v.w, acc[i].w);
+      if (dx) reinterpret_cast<float4*>(dx + r * (long long)K)[lane + 32 * i] = make_float4(g * wv[i].x, g * wv[i].y, g * wv[i].z, g * wv[i].w);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) reinterpret_cast<float4*>(sm[warp])[lane + 32 * i] = acc[i];
+  if (lane == 0) sb[warp] = bsum;
+  __syncthreads();
+  float* wsb = ws + (long long)blockIdx.x * (K + 1);
+  for (int c = threadIdx.x; c < K; c += blockDim.x) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) t += sm[k][c];
+    wsb[c] = t;
+  }
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) t += sb[k];
+    wsb[K] = t;
+  }
+}
+
 static inline int bwd_blocks(long long M) {
   long long nb = (M + kWarps - 1) / kWarps;
   if (nb > 4LL * kNumSMs) nb = 4LL * kNumSMs;
@@ -420,4 +490,40 @@ extern "C" int dost_colsum_planes(const void* hi, const void* lo, long long ld, 
   if (rc != DOST_OK) return rc;
   rbf::colsum_stage2_kernel<<<ceil_div(W, 32), 256, 0, st>>>((const float*)workspace, nch, W, out);
   return check_launch("colsum_planes stage2");
+}
+
+extern "C" int dost_rowdot_fwd(const float* x, long long ldx, const float* w, const float* bias, float* out, long long M, int K,
+                               dost_stream_t stream) {
+  DOST_REQUIRE(x && w && out && M > 0 && (K == 128 || K == 256 || K == 512) && al16(x) && al16(w) && ldx % 4 == 0, "rowdot_fwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)min64((M + rbf::kWarps - 1) / rbf::kWarps, 16LL * kNumSMs);
+  if (K == 128) rbf::rowdot_fwd_kernel<1><<<blocks, rbf::kWarps * 32, 0, st>>>(x, ldx, w, bias, out, M);
+  else if (K == 256) rbf::rowdot_fwd_kernel<2><<<blocks, rbf::kWarps * 32, 0, st>>>(x, ldx, w, bias, out, M);
+  else rbf::rowdot_fwd_kernel<4><<<blocks, rbf::kWarps * 32, 0, st>>>(x, ldx, w, bias, out, M);
+  return check_launch("rowdot_fwd");
+}
+
+extern "C" size_t dost_rowdot_bwd_workspace_bytes(long long M, int K) { return sizeof(float) * (size_t)rbf::bwd_blocks(M) * (K + 1); }
+
+extern "C" int dost_rowdot_bwd(const float* dout, const float* x, long long ldx, const float* w, float* dx, float* dwb, long long M,
+                               int K, void* workspace, size_t workspace_bytes, dost_stream_t stream) {
+  DOST_REQUIRE(dout && x && w && dwb && M > 0 && (K == 128 || K == 256 || K == 512) && al16(x) && al16(w) && al16(dx) && ldx % 4 == 0,
+               "rowdot_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = rbf::bwd_blocks(M);
+  const size_t need = sizeof(float) * (size_t)blocks * (K + 1);
+  if (!workspace || workspace_bytes < need) {
+    set_error("rowdot_bwd: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return DOST_ERR_WORKSPACE;
+  }
+  const long long rpb = (M + blocks - 1) / blocks;
+  float* ws = (float*)workspace;
+  if (K == 128) rbf::rowdot_bwd_kernel<1><<<blocks, rbf::kWarps * 32, 0, st>>>(dout, x, ldx, w, dx, ws, M, rpb);
+  else if (K == 256) rbf::rowdot_bwd_kernel<2><<<blocks, rbf::kWarps * 32, 0, st>>>(dout, x, ldx, w, dx, ws, M, rpb);
+  else rbf::rowdot_bwd_kernel<4><<<blocks, rbf::kWarps * 32, 0, st>>>(dout, x, ldx, w, dx, ws, M, rpb);
+  int rc = check_launch("rowdot_bwd");
+  if (rc != DOST_OK) return rc;
+  // partial rows are K + 1 wide: the fixed-order column reduction gives dw (columns 0..K-1) and db (column K)
+  rbf::colsum_stage2_kernel<<<ceil_div(K + 1, 32), 256, 0, st>>>(ws, blocks, K + 1, dwb);
+  return check_launch("rowdot_bwd reduce");
 }

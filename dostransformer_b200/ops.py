@@ -858,19 +858,29 @@ class _Linear(torch.autograd.Function):
         for si, ti in enumerate(spec.tensor_of_seg):
             xps.append(_planes_load(saved_planes[2 * si], saved_planes[2 * si + 1], ctx.in_rows[ti], ctx.in_cols[ti]))
         d_weight = None
+        Kp = _pad8(K)          # K % 8 != 0 only for a single segment: gradients are computed at the zero-padded width
         if needs[1]:
-            d_weight = torch.empty(N, K, dtype=torch.float32, device=dev)
+            d_weight = torch.empty(N, Kp, dtype=torch.float32, device=dev)
             k0 = 0
             for si, ti in enumerate(spec.tensor_of_seg):
                 w = ctx.in_cols[ti]
-                gemm_planes(M=N, N=w, K=M, a=[dvp], a_mode=L.MC, b=xps[si], b_mode=L.MC, out=d_weight[:, k0:k0 + w],
-                            split_k=_split_for(N, w, M))
+                wp_ = _pad8(w)
+                xb = xps[si] if wp_ == w else Planes(xps[si].hi, xps[si].lo, xps[si].rows, wp_)
+                gemm_planes(M=N, N=wp_, K=M, a=[dvp], a_mode=L.MC, b=xb, b_mode=L.MC, out=d_weight[:, k0:k0 + wp_],
+                            split_k=_split_for(N, wp_, M))
                 k0 += w
+            if Kp != K:
+                d_weight = d_weight[:, :K].contiguous()
         d_tensors: List[Optional[torch.Tensor]] = [None] * ctx.n_tensors
         tens_needs = needs[6:]
         if any(tens_needs):
-            dA = torch.empty(M, K, dtype=torch.float32, device=dev)
-            gemm_planes(M=M, N=K, K=N, a=[dvp], a_mode=L.KC, b=weight_planes(weight), b_mode=L.MC, out=dA)
+            dA = torch.empty(M, Kp, dtype=torch.float32, device=dev)
+            wpl = weight_planes(weight)
+            if Kp != K:
+                wpl = Planes(wpl.hi, wpl.lo, wpl.rows, Kp)
+            gemm_planes(M=M, N=Kp, K=N, a=[dvp], a_mode=L.KC, b=wpl, b_mode=L.MC, out=dA)
+            if Kp != K:
+                dA = dA[:, :K].contiguous()
             k0 = 0
             for si, ti in enumerate(spec.tensor_of_seg):
                 w = ctx.in_cols[ti]
@@ -880,9 +890,11 @@ class _Linear(torch.autograd.Function):
         return (None, d_weight, d_bias, d_slope, d_res, d_rowbias, *d_tensors)
 
 
-def planes_gemm_ok(M: int, N: int, K: int) -> bool:
-    """Problem sizes worth a 128 x N tensor-core tile whose operands satisfy the TMA alignment rules."""
-    return M >= 128 and N % 8 == 0 and K % 8 == 0 and M * N * K >= (1 << 22)
+def planes_gemm_ok(M: int, N: int, K: int, single_segment: bool = False) -> bool:
+    """Problem sizes worth a 128 x N tensor-core tile whose operands satisfy the TMA alignment rules.  A single-segment
+    operand may have any width: its planes are zero-padded to a multiple of 8 columns (e.g. the 41 Gaussian distance
+    features of the edge encoder) and the gradients are computed at the padded width."""
+    return M >= 128 and N % 8 == 0 and (K % 8 == 0 or single_segment) and M * N * max(K, 32) >= (1 << 22)
 
 
 def _linear_on_planes(spec: LinearSpec, weight: torch.Tensor, tensors) -> bool:
@@ -890,7 +902,7 @@ def _linear_on_planes(spec: LinearSpec, weight: torch.Tensor, tensors) -> bool:
     if not tc_active(weight) or os.environ.get("DOST_NO_LINPLANES"):
         return False
     N, K = weight.shape
-    if not planes_gemm_ok(spec.M, N, K):
+    if not planes_gemm_ok(spec.M, N, K, single_segment=len(spec.maps) == 1):
         return False
     if any(m is not None and (m.idx is not None or m.div != 1) for m in spec.maps):
         return False
@@ -948,12 +960,46 @@ def _map_adjoint(piece: torch.Tensor, m: Optional[RowMap], n_src_rows: int, acc:
     return segment_reduce_raw(cur, m.csr.rowptr, m.csr.perm, n_src_rows, out=acc, accumulate=True)
 
 
+class _RowDot(torch.autograd.Function):
+    """Linear(H -> 1): y[m] = x[m, :] . w + b as streaming kernels (out_layer, DOSTransformer.py:75,89)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        M, K = x.shape
+        out = torch.empty(M, 1, dtype=torch.float32, device=x.device)
+        L.check(L.lib().dost_rowdot_fwd(L.p(x), _ld(x), L.p(weight), L.p(bias), L.p(out), M, K, L.stream()), "rowdot_fwd")
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        x, weight = ctx.saved_tensors
+        M, K = x.shape
+        dev = x.device
+        d_out = d_out.contiguous()
+        dx = torch.empty(M, K, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        dwb = torch.empty(K + 1, dtype=torch.float32, device=dev)
+        lib = L.lib()
+        nb = lib.dost_rowdot_bwd_workspace_bytes(M, K)
+        ws = _ws(nb, dev)
+        L.check(lib.dost_rowdot_bwd(L.p(d_out), L.p(x), _ld(x), L.p(weight), L.p(dx), L.p(dwb), M, K, L.p(ws), nb, L.stream()),
+                "rowdot_bwd")
+        return dx, dwb[:K].view(1, K), (dwb[K:].view(1) if ctx.has_bias else None)
+
+
 def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: torch.Tensor,
            bias: Optional[torch.Tensor], *, M: Optional[int] = None, act: int = L.ACT_NONE, act_slope: float = 0.0,
            prelu_slope: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
            want_pre: bool = False, rowbias: Optional[torch.Tensor] = None, rowbias_div: int = 0):
     """Fused Linear.  ``segments`` are concatenated along the feature axis; a tensor may appear in several.
     ``rowbias`` [ceil(M / rowbias_div), N] is added to row m as rowbias[m // rowbias_div] (tensor-core path only)."""
+    if (weight.shape[0] == 1 and len(segments) == 1 and segments[0][1] is None and act == L.ACT_NONE and residual is None
+            and not want_pre and rowbias is None and weight.dtype == torch.float32 and weight.shape[1] in (128, 256, 512)
+            and weight.is_contiguous()):
+        x = segments[0][0]
+        if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
+            return _RowDot.apply(x, weight, bias)
     tensors: List[torch.Tensor] = []
     tos: List[int] = []
     for t, _ in segments:

