@@ -150,8 +150,8 @@ def cross_stack(enc: EnergyEncoderParams, q, x_nodes, graph: ops.CrystalGraph, S
     for layer in enc.layers:
         ln0 = layer.layer_norms[0]
         kv = ops.layer_norm(x_nodes, ln0.weight, ln0.bias)
-        q_ln = ops.layer_norm(q, ln0.weight, ln0.bias, want_planes=q.dim() == 3)
-        y = ops.cross_attention(q_ln, kv, ln0.bias, q, graph, S, seeds.p, seeds.next())
+        q_ln, q_res = ops.layer_norm(q, ln0.weight, ln0.bias, want_planes=q.dim() == 3, with_residual=True)
+        y = ops.cross_attention(q_ln, kv, ln0.bias, q_res, graph, S, seeds.p, seeds.next())
         q = _ffn(layer, y.view(S * T, H)).view(S, T, H)
     return ops.layer_norm(q, enc.layer_norm.weight, enc.layer_norm.bias)
 
@@ -162,9 +162,13 @@ def self_stack(enc: EnergyEncoderParams, x0, seeds: _Seeds):
     x = x0
     for li, layer in enumerate(enc.layers):
         ln0 = layer.layer_norms[0]
-        k = ops.layer_norm(x0, ln0.weight, ln0.bias, want_planes=True)
-        q = k if li == 0 else ops.layer_norm(x, ln0.weight, ln0.bias, want_planes=True)
-        y = ops.self_attention(q, k, x, seeds.p, seeds.next())
+        if li == 0:
+            k, x_res = ops.layer_norm(x0, ln0.weight, ln0.bias, want_planes=True, with_residual=True)
+            q = k
+        else:
+            k = ops.layer_norm(x0, ln0.weight, ln0.bias, want_planes=True)
+            q, x_res = ops.layer_norm(x, ln0.weight, ln0.bias, want_planes=True, with_residual=True)
+        y = ops.self_attention(q, k, x_res, seeds.p, seeds.next())
         x = _ffn(layer, y.view(S * T, H)).view(S, T, H)
     return ops.layer_norm(x, enc.layer_norm.weight, enc.layer_norm.bias)
 

@@ -1022,45 +1022,61 @@ def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: to
 # LayerNorm (+PReLU)
 # =====================================================================================================
 class _LayerNorm(torch.autograd.Function):
+    """outputs: y [, planes hi, lo] [, x passed through].  The pass-through output lets a residual block
+    ``out = x + f(LN(x))`` hand BOTH uses of x to this node: backward then adds the residual gradient inside the LayerNorm
+    backward kernel (``dres``) instead of autograd launching a separate add over the [S, T, H] stream."""
+
     @staticmethod
-    def forward(ctx, x, gamma, beta, slope, want_planes=False):
+    def forward(ctx, x, gamma, beta, slope, want_planes=False, with_residual=False):
         x2 = x.reshape(-1, x.shape[-1])
         if x2.stride(-1) != 1:
             x2 = x2.contiguous()
         M, W = x2.shape
         ctx.vec = x.dtype == torch.float32 and planes_ok(W) and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0 \
             and not os.environ.get("DOST_NO_LNVEC")
-        ctx.with_planes = False
+        ctx.n_planes = 0
+        ctx.with_residual = with_residual
+        ctx.shape = x.shape
+        outs = []
         if ctx.vec:       # 16-byte vectorised fp32 kernels (rows_bf.cu)
             y, pl, stats = ln_fwd_planes(x2, gamma, beta, slope, want_y=True, want_planes=want_planes)
-            ctx.save_for_backward(x2, gamma, beta, slope, stats)
-            ctx.shape = x.shape
+            outs.append(y.view(x.shape))
             if want_planes:
-                ctx.with_planes = True
+                ctx.n_planes = 2
                 lo = pl.lo if pl.lo is not None else pl.hi
                 ctx.mark_non_differentiable(pl.hi, lo)
-                ctx.set_materialize_grads(False)
-                return y.view(x.shape), pl.hi, lo
-            return y.view(x.shape)
-        assert not want_planes
-        y = torch.empty(M, W, dtype=x.dtype, device=x.device)
-        stats = torch.empty(M, 2, dtype=x.dtype, device=x.device)
-        L.check(L.lib().dost_ln_fwd(L.dt(x), L.p(x2), _ld(x2), L.p(gamma), L.p(beta), L.p(slope), L.p(y), L.p(stats), M, W,
-                                    L.stream()), "ln_fwd")
+                outs += [pl.hi, lo]
+        else:
+            assert not want_planes
+            y = torch.empty(M, W, dtype=x.dtype, device=x.device)
+            stats = torch.empty(M, 2, dtype=x.dtype, device=x.device)
+            L.check(L.lib().dost_ln_fwd(L.dt(x), L.p(x2), _ld(x2), L.p(gamma), L.p(beta), L.p(slope), L.p(y), L.p(stats), M, W,
+                                        L.stream()), "ln_fwd")
+            outs.append(y.view(x.shape))
         ctx.save_for_backward(x2, gamma, beta, slope, stats)
-        ctx.shape = x.shape
-        return y.view(x.shape)
+        ctx.set_materialize_grads(False)
+        if with_residual:
+            outs.append(x.view_as(x))
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, dy, *_unused):
+    def backward(ctx, dy, *rest):
         x2, gamma, beta, slope, stats = ctx.saved_tensors
         M, W = x2.shape
+        d_res = rest[ctx.n_planes] if ctx.with_residual else None
+        if d_res is not None:
+            d_res = d_res.reshape(M, W)
+            if d_res.stride(-1) != 1:
+                d_res = d_res.contiguous()
+        if dy is None:                    # only the pass-through was used downstream
+            return (d_res.view(ctx.shape) if d_res is not None else None), None, None, None, None, None
         dy2 = dy.reshape(M, W)
         if dy2.stride(-1) != 1:
             dy2 = dy2.contiguous()
-        if ctx.vec and dy2.stride(0) % 4 == 0 and dy2.data_ptr() % 16 == 0:
-            dx, _, dg, db, ds, _ = ln_bwd_planes(dy2, x2, stats, gamma, beta, slope)
-            return dx.view(ctx.shape), dg, db, ds, None
+        if ctx.vec and dy2.stride(0) % 4 == 0 and dy2.data_ptr() % 16 == 0 and \
+                (d_res is None or (d_res.stride(0) % 4 == 0 and d_res.data_ptr() % 16 == 0)):
+            dx, _, dg, db, ds, _ = ln_bwd_planes(dy2, x2, stats, gamma, beta, slope, dres=d_res)
+            return dx.view(ctx.shape), dg, db, ds, None, None
         dev, dtype = x2.device, x2.dtype
         dx = torch.empty(M, W, dtype=dtype, device=dev)
         dg = torch.empty(W, dtype=dtype, device=dev)
@@ -1071,20 +1087,29 @@ class _LayerNorm(torch.autograd.Function):
         ws = _ws(nb, dev)
         L.check(lib.dost_ln_bwd(L.dt(x2), L.p(dy2), _ld(dy2), L.p(x2), _ld(x2), L.p(stats), L.p(gamma), L.p(beta),
                                 L.p(slope), L.p(dx), L.p(dg), L.p(db), L.p(ds), M, W, L.p(ws), nb, L.stream()), "ln_bwd")
-        return dx.view(ctx.shape), dg, db, ds, None
+        if d_res is not None:
+            out = torch.empty_like(dx)
+            _axpy2(dx, d_res, out)
+            dx = out
+        return dx.view(ctx.shape), dg, db, ds, None, None
 
 
-def layer_norm(x, gamma, beta, prelu_slope=None, want_planes: bool = False):
+def layer_norm(x, gamma, beta, prelu_slope=None, want_planes: bool = False, with_residual: bool = False):
     """LayerNorm (+PReLU).  want_planes: also emit the result as GEMM operand planes (attached to the returned tensor as
-    ``_dost_planes``; only on the vectorised fp32 path)."""
+    ``_dost_planes``; only on the vectorised fp32 path).  with_residual: returns (LN(x), x) where the second output is x
+    routed through this node, to be used as the residual operand of the block (see _LayerNorm)."""
+    planes = False
     if want_planes and x.dtype == torch.float32 and planes_ok(x.shape[-1]) and tc_active(x) and \
             not os.environ.get("DOST_NO_LNVEC"):
         x2 = x.reshape(-1, x.shape[-1])
-        if x2.stride(-1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0:
-            y, hi, lo = _LayerNorm.apply(x, gamma, beta, prelu_slope, True)
-            y._dost_planes = Planes(hi, lo if _with_lo() else None, x2.shape[0], x2.shape[1])
-            return y
-    return _LayerNorm.apply(x, gamma, beta, prelu_slope, False)
+        planes = x2.stride(-1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0
+    res = _LayerNorm.apply(x, gamma, beta, prelu_slope, planes, with_residual)
+    if not planes and not with_residual:
+        return res
+    y = res[0]
+    if planes:
+        y._dost_planes = Planes(res[1], res[2] if _with_lo() else None, x.numel() // x.shape[-1], x.shape[-1])
+    return (y, res[-1]) if with_residual else y
 
 
 # =====================================================================================================
