@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kWarps * 32) rowdot_bwd_kernel(const float* __
 
 static inline int bwd_blocks(long long M) {
   long long nb = (M + kWarps - 1) / kWarps;
-  if (nb > 4LL * kNumSMs) nb = 4LL * kNumSMs;
+  if (nb > 2LL * kNumSMs) nb = 2LL * kNumSMs;     // 2 resident blocks per SM; fewer partial rows for the second stage
   if (nb < 1) nb = 1;
   return (int)nb;
 }
