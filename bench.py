@@ -98,8 +98,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_batches(rank: int, nb: int, B: int):
-    from dostransformer_b200.synthetic import make_edos_batch
+def make_batches(rank: int, nb: int, B: int, workload: str = "edos"):
+    from dostransformer_b200.synthetic import make_edos_batch, make_large_cell_batch
+    if workload == "large":      # BASELINE configs[3]: 200-400 atoms per crystal, 24 neighbours (not the headline line)
+        return [make_large_cell_batch(B, seed=4000 + 1000 * rank + i) for i in range(nb)]
     return [make_edos_batch(B, seed=2000 + 1000 * rank + i) for i in range(nb)]
 
 
@@ -271,7 +273,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
     pk = peaks()
     B = args.batch
     NB = 3
-    host = [b.pin_memory() for b in make_batches(rank if args.data_rank < 0 else args.data_rank, NB, B)]
+    host = [b.pin_memory() for b in make_batches(rank if args.data_rank < 0 else args.data_rank, NB, B, args.workload)]
     nmax = max(int(torch.bincount(b.batch).max()) for b in host)
     n_nodes = sum(b.batch.numel() for b in host) / NB
     n_edges = sum(b.edge_index.shape[1] for b in host) / NB
@@ -354,8 +356,11 @@ def run_product(args, rank: int, world: int, local_rank: int):
         "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x3": "bf16x3 operands, f32 accumulate", "bf16": "bf16 operands, f32 accumulate"}[
             args.precision], "data": "synthetic",
-        "config": {"workload": f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, random-split shape "
-                               f"(BASELINE configs[1]/[2]), {B} crystals per GPU", "crystals_per_gpu": B,
+        "config": {"workload": (f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, random-split shape "
+                                f"(BASELINE configs[1]/[2]), {B} crystals per GPU") if args.workload == "edos" else
+                               (f"eDOS DOSTransformer hidden={HIDDEN} L={GNN_LAYERS} t={T_LAYERS} T={T}, large-cell stress shape "
+                                f"(BASELINE configs[3]: 200-400 atoms, 24 neighbours), {B} crystals per GPU"),
+                   "crystals_per_gpu": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "mean_nodes_per_batch": n_nodes,
                    "mean_edges_per_batch": n_edges, "nmax": nmax, "precision": PREC_DESC[args.precision],
                    "l2_policy": "3 distinct batches rotated; per-step activations (>1 GB) exceed the 126 MB L2"},
@@ -453,6 +458,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed CPU baseline steps (bounded sample, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the extra bf16-mode measurement")
+    ap.add_argument("--workload", default="edos", choices=["edos", "large"],
+                    help="edos = the headline configuration; large = BASELINE configs[3] (use --batch 64)")
     ap.add_argument("--nmax", type=int, default=0, help="(experiments) force a larger global padding length")
     ap.add_argument("--data-rank", type=int, default=-1, help="(experiments) generate the batches of another rank")
     ap.add_argument("--precision", default=os.environ.get("DOST_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
