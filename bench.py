@@ -340,33 +340,13 @@ def run_product(args, rank: int, world: int, local_rank: int):
 
     # ---------------------------------------------------------------- end-to-end timing (host batches)
     h2d = host[0].nbytes()
-    copy_stream = torch.cuda.Stream(device=dev)
-
-    def fetch(i):
-        """H2D of batch i from pinned memory on the copy stream (what a pin_memory DataLoader + non_blocking .to() does)."""
-        with torch.cuda.stream(copy_stream):
-            g = _to_device(host[i % NB], dev)
-            ev = copy_stream.record_event()
-        for k in g.keys():
-            v = getattr(g, k)
-            if torch.is_tensor(v):
-                v.record_stream(st)
-        return g, ev
-
     for i in range(min(2, args.warmup)):
-        g, ev = fetch(i)
-        st.wait_event(ev)
-        step(g).item()
+        step(_to_device(host[i % NB], dev)).item()
     barrier()
     t0 = time.perf_counter()
-    nxt = fetch(0)
     for i in range(args.steps):
-        g, ev = nxt
-        st.wait_event(ev)
-        loss = step(g)
-        if i + 1 < args.steps:
-            nxt = fetch(i + 1)                          # the next batch's H2D overlaps this step's kernels
-        loss.item()                                     # D2H of the step's result, every step
+        loss = step(_to_device(host[i % NB], dev))      # H2D of the whole batch from pinned memory
+        loss.item()                                     # D2H of the step's result
     barrier()
     e2e_sec = time.perf_counter() - t0
     if world > 1:
@@ -395,8 +375,8 @@ def run_product(args, rank: int, world: int, local_rank: int):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_sec / args.steps * 1e3,
-                "api": "DOSTransformer(batch) + ops.dos_loss + loss.backward(); every batch is copied from pinned host memory "
-                       "inside the timed region (on a copy stream, overlapping the previous step), loss.item() every step"},
+                "api": "DOSTransformer(batch) + ops.dos_loss + loss.backward(), batch copied from pinned host memory, "
+                       "loss.item() every step"},
     }
     fl = 3.0 * B * flops_per_crystal_fwd(n_nodes / B, n_edges / B, nmax)
     line["model_tflops"] = fl * args.steps / sec / 1e12
