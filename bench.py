@@ -17,6 +17,7 @@ oracle/dost_oracle.py restates it and is pinned against it by tests/golden) on t
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -340,13 +341,21 @@ def run_product(args, rank: int, world: int, local_rank: int):
 
     # ---------------------------------------------------------------- end-to-end timing (host batches)
     h2d = host[0].nbytes()
-    for i in range(min(2, args.warmup)):
+    for i in range(max(NB, min(2, args.warmup))):       # every distinct batch shape once: allocator warm-up
         step(_to_device(host[i % NB], dev)).item()
+    # Long-lived objects (model, batches, autograd metadata) leave the cyclic GC's working set: without this a
+    # generation-2 collection lands inside the synchronous loop every few steps and stalls one step by 10-70 ms
+    # (the device-resident loop above hides such pauses behind the launch queue).
+    gc.collect()
+    gc.freeze()
     barrier()
+    per_step = []
     t0 = time.perf_counter()
     for i in range(args.steps):
+        ts = time.perf_counter()
         loss = step(_to_device(host[i % NB], dev))      # H2D of the whole batch from pinned memory
         loss.item()                                     # D2H of the step's result
+        per_step.append((time.perf_counter() - ts) * 1e3)
     barrier()
     e2e_sec = time.perf_counter() - t0
     if world > 1:
@@ -374,9 +383,9 @@ def run_product(args, rank: int, world: int, local_rank: int):
                    "l2_policy": "3 distinct batches rotated; per-step activations (>1 GB) exceed the 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_sec / args.steps * 1e3,
+                "ms_per_step": e2e_sec / args.steps * 1e3, "ms_each_step": [round(x, 2) for x in per_step],
                 "api": "DOSTransformer(batch) + ops.dos_loss + loss.backward(), batch copied from pinned host memory, "
-                       "loss.item() every step"},
+                       "loss.item() every step; gc.freeze() after warm-up"},
     }
     fl = 3.0 * B * flops_per_crystal_fwd(n_nodes / B, n_edges / B, nmax)
     line["model_tflops"] = fl * args.steps / sec / 1e12

@@ -172,11 +172,17 @@ def load(path: str = LIB_PATH) -> C.CDLL:
     return lib
 
 
+_cuda_checked = False
+
+
 def lib() -> C.CDLL:
-    """The loaded library, for compute calls: requires a visible CUDA device."""
-    L = load()
-    if not torch.cuda.is_available():
-        raise RuntimeError("dostransformer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    """The loaded library, for compute calls: requires a visible CUDA device (checked once per process)."""
+    global _cuda_checked
+    L = _lib if _lib is not None else load()
+    if not _cuda_checked:
+        if not torch.cuda.is_available():
+            raise RuntimeError("dostransformer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        _cuda_checked = True
     return L
 
 
@@ -203,8 +209,31 @@ def p(t: Optional[torch.Tensor]):
     return C.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
 def stream():
+    """cudaStream_t of torch's current stream on the current device (the raw-pointer query is ~10x cheaper than
+    building a torch.cuda.Stream object; it is called once per kernel launch)."""
+    if _raw_stream is not None and _get_device is not None:
+        return _raw_stream(_get_device())
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_switches = {}
+
+
+def switch(name: str) -> bool:
+    """Environment switch (DOST_NO_*), read once per process; reload_switches() re-reads them."""
+    v = _switches.get(name)
+    if v is None:
+        v = _switches[name] = bool(os.environ.get(name))
+    return v
+
+
+def reload_switches() -> None:
+    _switches.clear()
 
 
 def launch_count() -> int:

@@ -105,7 +105,7 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
     n_layers = len(processors)
     H = x.shape[1]
     blocked = ops.tc_active(x) and ops.planes_ok(2 * H) and H % 64 == 0 and graph.E >= 128 and \
-        not os.environ.get("DOST_NO_EDGEBLOCK") and \
+        not L.switch("DOST_NO_EDGEBLOCK") and \
         (graph.by_src is not None or not torch.is_grad_enabled())
     for i, proc in enumerate(processors):
         last = i == n_layers - 1
@@ -126,7 +126,7 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
 
 def _ffn(layer, y2d):
     ln1 = layer.layer_norms[1]
-    if ops.tc_active(y2d) and ops.planes_ok(y2d.shape[1]) and y2d.shape[0] >= 128 and not os.environ.get("DOST_NO_FFNBLOCK"):
+    if ops.tc_active(y2d) and ops.planes_ok(y2d.shape[1]) and y2d.shape[0] >= 128 and not L.switch("DOST_NO_FFNBLOCK"):
         return ops.ffn_block(y2d, ln1.weight, ln1.bias, layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias)
     h = ops.layer_norm(y2d, ln1.weight, ln1.bias)
     h = ops.linear([(h, None)], layer.fc1.weight, layer.fc1.bias, act=L.ACT_RELU)
@@ -187,7 +187,7 @@ def dos_heads(model, x_nodes, graph: ops.CrystalGraph, graph_vec, prompt_table, 
         h = cross_stack(model.transformer_source, h, x_nodes, graph, B, T, seeds)
         return ops.linear([(h.view(B * T, H), None)], model.out_layer.weight, model.out_layer.bias).view(B, T)
 
-    if ops.tc_active(e2d) and ops.planes_gemm_ok(B * T, H, H) and not os.environ.get("DOST_NO_HEADSPLIT"):
+    if ops.tc_active(e2d) and ops.planes_gemm_ok(B * T, H, H) and not L.switch("DOST_NO_HEADSPLIT"):
         # split weights: the per-crystal terms (graph vector, prompt embedding) are multiplied once per crystal and enter
         # the [B*T, H] GEMM as a row-group bias instead of being broadcast over the T energy tokens
         wf, wp = model.fc.weight, model.fc_prompt.weight

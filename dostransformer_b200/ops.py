@@ -899,7 +899,7 @@ def planes_gemm_ok(M: int, N: int, K: int, single_segment: bool = False) -> bool
 
 def _linear_on_planes(spec: LinearSpec, weight: torch.Tensor, tensors) -> bool:
     """Plain (un-mapped) fp32 segments of TMA-friendly widths go to the TMA-fed tensor-core kernel."""
-    if not tc_active(weight) or os.environ.get("DOST_NO_LINPLANES"):
+    if not tc_active(weight) or L.switch("DOST_NO_LINPLANES"):
         return False
     N, K = weight.shape
     if not planes_gemm_ok(spec.M, N, K, single_segment=len(spec.maps) == 1):
@@ -1033,7 +1033,7 @@ class _LayerNorm(torch.autograd.Function):
             x2 = x2.contiguous()
         M, W = x2.shape
         ctx.vec = x.dtype == torch.float32 and planes_ok(W) and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0 \
-            and not os.environ.get("DOST_NO_LNVEC")
+            and not L.switch("DOST_NO_LNVEC")
         ctx.n_planes = 0
         ctx.with_residual = with_residual
         ctx.shape = x.shape
@@ -1100,7 +1100,7 @@ def layer_norm(x, gamma, beta, prelu_slope=None, want_planes: bool = False, with
     routed through this node, to be used as the residual operand of the block (see _LayerNorm)."""
     planes = False
     if want_planes and x.dtype == torch.float32 and planes_ok(x.shape[-1]) and tc_active(x) and \
-            not os.environ.get("DOST_NO_LNVEC"):
+            not L.switch("DOST_NO_LNVEC"):
         x2 = x.reshape(-1, x.shape[-1])
         planes = x2.stride(-1) == 1 and x2.stride(0) % 4 == 0 and x2.data_ptr() % 16 == 0
     res = _LayerNorm.apply(x, gamma, beta, prelu_slope, planes, with_residual)
@@ -1267,7 +1267,7 @@ class _CrossAttentionTC(torch.autograd.Function):
 def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float = 0.0, seed: int = 0):
     H = kv.shape[1]
     if (tc_active(kv) and H % 128 == 0 and drop_p == 0.0 and S == graph.B and graph.nmax_host is not None
-            and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not os.environ.get("DOST_NO_XATTN_TC")):
+            and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")):
         return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q))
     return _CrossAttention.apply(q, kv, phantom, resid, graph, S, drop_p, seed)
 
@@ -1287,7 +1287,7 @@ class _SelfAttention(torch.autograd.Function):
         dev, dtype = q.device, q.dtype
         Lp = (Lk + 3) // 4 * 4          # padded row length of the score matrices: keeps 16-byte vector loads legal
         scores = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
-        ctx.on_planes = tc_active(q) and H % 8 == 0 and Lq * Lk * H >= (1 << 18) and not os.environ.get("DOST_NO_ATTNPLANES")
+        ctx.on_planes = tc_active(q) and H % 8 == 0 and Lq * Lk * H >= (1 << 18) and not L.switch("DOST_NO_ATTNPLANES")
         if ctx.on_planes:
             # the four batched contractions on the TMA-fed tensor-core kernel (3-D tensor maps, one batch per sequence)
             qp = qpl if qpl is not None else split_planes(q.view(S * Lq, H))

@@ -1,7 +1,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from dostransformer_b200 import ops
+from dostransformer_b200 import _lib, ops
 from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
 from dostransformer_b200.synthetic import make_edos_batch
 DEV = "cuda"
@@ -22,6 +22,7 @@ for t in toggles:
         if k.startswith("DOST_NO_"): del os.environ[k]
     for k in t.split("+"):
         if k: os.environ[k] = "1"
+    _lib.reload_switches()
     got = run("bf16x3")
     errs = sorted(((((got[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-30)).item(), k) for k in ref), reverse=True)
     print(f"[{t or 'all on'}] worst:", ", ".join(f"{k}={e:.1e}" for e, k in errs[:4]))
