@@ -828,3 +828,59 @@ def test_rowdot_linear_to_one(K):
     o2, g2 = _grads(lambda: torch.nn.functional.linear(x.double(), w.double(), b.double()), [x, w, b])
     for a_, b_ in zip(o1 + g1, o2 + g2):
         assert relerr(a_, b_) < 2e-5
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-5), ("bf16", 1e-2)])
+def test_planes_gemm_batched_and_ragged(prec, tol):
+    """3-D tensor maps (one problem per batch entry, boxes never span problems) and ragged problems: per-problem row
+    offsets into one B plane, and per-problem output row offset / row limit."""
+    torch.manual_seed(17)
+    S, Mq, Kd, H = 7, 201, 96, 128
+    with ops.precision(prec):
+        # ---- plain batched: C[z] = A[z] B[z]^T with M, N not multiples of the tile
+        a = torch.randn(S, Mq, Kd, device=DEV)
+        b = torch.randn(S, 77, Kd, device=DEV)
+        ap, bp = ops.split_planes(a.view(S * Mq, Kd)), ops.split_planes(b.view(S * 77, Kd))
+        Np = 80
+        out = torch.full((S, Mq, Np), float("nan"), device=DEV)
+        ops.gemm_planes(M=Mq, N=Np, K=Kd, a=[ap], a_mode=L.KC, b=bp, b_mode=L.KC, b_rows=77, out=out.view(S * Mq, Np), batch=S,
+                        a_bstride=Mq * ap.ld, b_bstride=77 * bp.ld, c_bstride=Mq * Np)
+        ref = torch.einsum("smk,snk->smn", a.double(), b.double())
+        assert (out[:, :, :77].double() - ref).abs().max() / ref.abs().max() < tol
+        assert torch.all(out[:, :, 77:] == 0)          # columns past the problem's B rows read zero-filled rows
+        # ---- ragged B: problem z uses rows off[z] .. off[z] + n[z] of ONE plane (K-major and MN-major use)
+        n = torch.tensor([5, 33, 64, 1, 17, 40, 9])
+        off = torch.cat([torch.zeros(1, dtype=torch.long), n.cumsum(0)])
+        Ntot, npad = int(off[-1]), 64
+        keys = torch.randn(Ntot, H, device=DEV)
+        q = torch.randn(S, Mq, H, device=DEV)
+        kp, qp = ops.split_planes(keys), ops.split_planes(q.view(S * Mq, H))
+        offd = off[:-1].to(torch.int32).to(DEV)
+        sc = torch.empty(S * Mq, npad, device=DEV)
+        ops.gemm_planes(M=Mq, N=npad, K=H, a=[qp], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Ntot, out=sc, batch=S,
+                        a_bstride=Mq * qp.ld, c_bstride=Mq * npad, b_rowoff=offd)
+        sc = sc.view(S, Mq, npad)
+        for z in range(S):
+            ref = q[z].double() @ keys[off[z]:off[z] + n[z]].double().T
+            assert (sc[z, :, :n[z]].double() - ref).abs().max() / ref.abs().max() < tol, z
+        # P V with P zero past each problem's own keys: rows of the next problem contribute nothing
+        p = torch.rand(S, Mq, npad, device=DEV)
+        for z in range(S):
+            p[z, :, n[z]:] = 0
+        pp = ops.split_planes(p.view(S * Mq, npad))
+        o = torch.empty(S * Mq, H, device=DEV)
+        ops.gemm_planes(M=Mq, N=H, K=npad, a=[pp], a_mode=L.KC, b=kp, b_mode=L.MC, b_rows=Ntot, out=o, batch=S,
+                        a_bstride=Mq * pp.ld, c_bstride=Mq * H, b_rowoff=offd)
+        o = o.view(S, Mq, H)
+        for z in range(S):
+            ref = p[z, :, :n[z]].double() @ keys[off[z]:off[z] + n[z]].double()
+            assert (o[z].double() - ref).abs().max() / ref.abs().max() < tol, z
+        # ---- ragged output: dK[off[z] + j] = sum_t P[z, t, j] q[z, t]  for j < n[z], nothing else is written
+        dk = torch.full((Ntot, H), 7.0, device=DEV)
+        nd = n.to(torch.int32).to(DEV)
+        ops.gemm_planes(M=npad, N=H, K=Mq, a=[pp], a_mode=L.MC, b=qp, b_mode=L.MC, out=dk, batch=S, a_bstride=Mq * pp.ld,
+                        b_bstride=Mq * qp.ld, c_rowoff=offd, c_rowlim=nd)
+        for z in range(S):
+            ref = p[z, :, :n[z]].double().T @ q[z].double()
+            got = dk[off[z]:off[z] + n[z]].double()
+            assert (got - ref).abs().max() / ref.abs().max() < tol, z
