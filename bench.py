@@ -426,6 +426,11 @@ def run_product(args, rank: int, world: int, local_rank: int):
         line["optimizer"] = {"kind": "dost_adamw_step (fused multi-tensor AdamW, lr 1e-4, wd 1e-2)", "ms_per_step": oms,
                              "live_parameters": nlive, "gbytes_per_s": 28.0 * nlive / (oms * 1e-3) / 1e9}
         torch.manual_seed(0)     # the optimizer steps above moved the weights; nothing below depends on their values
+    if world == 1:
+        try:
+            line["device_collate"] = device_collate_bench(host, dev, B, step, args.steps)
+        except Exception as ex:
+            line["device_collate"] = {"error": repr(ex)}
     if world == 1 and args.precision == "bf16x3" and not args.no_alt:
         # the same step with plain bf16 operands (hi plane only), for reference: stated tolerance 5e-2 on gradients
         model.precision = "bf16"
@@ -457,6 +462,44 @@ def run_product(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def device_collate_bench(host, dev, B, step, steps):
+    """the batches' crystals packed once into HBM-resident tables; a step sends B crystal ids and the batch is
+    assembled on the device (csrc/collate.cu).  Reports the assembly alone (CUDA events, bytes = read + written) and the
+    end-to-end step that starts from host ids."""
+    from dostransformer_b200.collate import PackedCrystals, split_batch
+    graphs = [g for b in host for g in split_batch(b)]
+    pk = PackedCrystals.from_graphs(graphs, device=dev)
+    gen = torch.Generator().manual_seed(7)
+    ids = [torch.randperm(len(pk), generator=gen)[:B].pin_memory() for _ in range(6)]
+    for i in ids[:3]:
+        b = pk.collate(i)
+    torch.cuda.synchronize()
+    st = torch.cuda.current_stream()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 30
+    c0.record(st)
+    for r in range(reps):
+        b = pk.collate(ids[r % len(ids)])
+    c1.record(st)
+    torch.cuda.synchronize()
+    cms = c0.elapsed_time(c1) / reps
+    nbytes = 2.0 * b.nbytes()
+    for i in ids:                                       # every batch shape once: allocator warm-up
+        step(pk.collate(i)).item()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for r in range(steps):
+        g = pk.collate(ids[r % len(ids)])
+        step(g).item()
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    return {"value": B * steps / sec, "unit": UNIT, "ms_per_step": sec / steps * 1e3, "h2d_bytes_per_step": 8 * B,
+            "d2h_bytes_per_step": 4, "collate_ms": cms, "collate_gbytes_per_s": nbytes / (cms * 1e-3) / 1e9,
+            "collate_launches": len(pk.tables) + 2, "store_bytes": pk.nbytes(), "crystals_in_store": len(pk),
+            "note": "crystal ids from host memory -> PackedCrystals.collate (segmented copies on the device) -> fwd+bwd; "
+                    "collate_ms includes the host-side launch cost of its kernels"}
 
 
 def _to_device(g, dev):

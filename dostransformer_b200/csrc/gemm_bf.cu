@@ -127,7 +127,9 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+  // relaxed: the arrive only says "this warp's tcgen05.ld of the accumulator has completed" (tcgen05.wait::ld has returned);
+  // a release at cluster scope would cost a MEMBAR.ALL.GPU that waits for every global store the epilogue has in flight
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
@@ -185,6 +187,43 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// Predicated global accesses for the epilogue's row tails: a guarded `if (row_ok) *p = v;` compiles to a branch around its
+// own basic block (address arithmetic included), eight of them per feature; these stay straight-line code.
+__device__ __forceinline__ void stg128_if(float* p, float a, float b, float c, float d, bool ok) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}" ::"l"(p), "f"(a),
+               "f"(b), "f"(c), "f"(d), "r"((uint32_t)ok)
+               : "memory");
+}
+__device__ __forceinline__ void stg64_if(void* p, uint32_t a, uint32_t b, bool ok) {
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q st.global.v2.b32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(a), "r"(b),
+               "r"((uint32_t)ok)
+               : "memory");
+}
+__device__ __forceinline__ float4 ldg128_nc_if(const float* p, bool ok) {      // read-only data (residual, row bias)
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+               : "l"(p), "r"((uint32_t)ok)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldg128_if(const float* p, bool ok) {         // data this kernel also writes (accumulate)
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.v4.f32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+               : "l"(p), "r"((uint32_t)ok)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ldg64_nc_if(const void* p, bool ok) {
+  uint2 v = make_uint2(0u, 0u);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
+               : "+r"(v.x), "+r"(v.y)
+               : "l"(p), "r"((uint32_t)ok)
+               : "memory");
   return v;
 }
 
@@ -398,6 +437,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     const uint32_t stg = smem_u32(epi_smem) + warp * 4096;  // this warp's 32 x 32 fp32 staging tile (128-byte rows)
     const int rsub = lane >> 3, cj = lane & 7;             // after the transpose: rows rsub + 4 i, 16-byte column chunk cj
     const uint32_t acce_remote0 = CTA2 ? mapa_rank(acce0, 0) : 0u;   // the leader's accumulator-empty barriers
+    // Feature switches and the hot pointers / strides live in registers for the whole kernel: read from the parameter
+    // bank inside the chunk loop, every `if (p.x)` is a constant load + dependent branch (~a dozen serialised
+    // round trips per chunk with only two epilogue warps per scheduler to hide them).  The empty asm statements keep the
+    // compiler from rematerialising the loads.
+    enum : uint32_t { F_BIAS = 1, F_ROWBIAS = 2, F_PRE = 4, F_ACT = 8, F_DACT = 16, F_RES = 32, F_OUT = 64, F_ACC = 128,
+                      F_HI = 256, F_LO = 512, F_COLPART = 1024, F_SPLITK = 2048, F_ROWLIM = 4096 };
+    uint32_t feat = (p.bias ? F_BIAS : 0u) | (p.rowbias ? F_ROWBIAS : 0u) | (p.out_pre ? F_PRE : 0u) |
+                    (p.act != DOST_ACT_NONE ? F_ACT : 0u) | (p.dact_hi ? F_DACT : 0u) | (p.residual ? F_RES : 0u) |
+                    (p.out ? F_OUT : 0u) | (p.accumulate ? F_ACC : 0u) | (p.out_hi ? F_HI : 0u) | (p.out_lo ? F_LO : 0u) |
+                    (p.colpart ? F_COLPART : 0u) | (p.zmode == 2 ? F_SPLITK : 0u) | (p.c_rowlim ? F_ROWLIM : 0u);
+    int Mv = p.M, Nv = p.N;
+    long long ldc_v = p.ldc, ldop_v = p.ld_op, ldres_v = p.ld_res;
+    const float* bias_v = p.bias;
+    const float* res_v = p.residual;
+    float* out_v = p.out;
+    __nv_bfloat16* hi_v = p.out_hi;
+    __nv_bfloat16* lo_v = p.out_lo;
+    asm volatile("" : "+r"(feat), "+r"(Mv), "+r"(Nv));
+    asm volatile("" : "+l"(ldc_v), "+l"(ldop_v), "+l"(ldres_v));
+    asm volatile("" : "+l"(bias_v), "+l"(res_v), "+l"(out_v), "+l"(hi_v), "+l"(lo_v));
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++local) {
       const TileInfo t = tile_info<BN, CTA2>(p, tile, rank);
       const int buf = local & 1;
@@ -436,108 +495,106 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         }
         __syncwarp();                                      // staging tile may be overwritten by the next chunk
         const int n = nbase + c0;
-        if (n >= p.N || t.m0 + quad * 32 >= p.M) continue;  // N % 4 == 0: a thread's 4 columns are all in or all out
+        if (n >= Nv || t.m0 + quad * 32 >= Mv) continue;    // N % 4 == 0: a thread's 4 columns are all in or all out
         bool mok[8];
-        const int mlim = p.c_rowlim ? min(p.M, __ldg(p.c_rowlim + t.z)) : p.M;
+        const int mlim = (feat & F_ROWLIM) ? min(Mv, __ldg(p.c_rowlim + t.z)) : Mv;
 #pragma unroll
         for (int i = 0; i < 8; ++i) mok[i] = mbase + 4 * i < mlim;
-        if (p.zmode == 2) {
-          float* ws = p.ws + ((long long)t.z * p.M + mbase) * p.N + n;
+        if (feat & F_SPLITK) {
+          float* ws = p.ws + ((long long)t.z * Mv + mbase) * Nv + n;
+          const bool empty = t.nkt == 0;                    // an empty K slice contributes zeros (its TMEM is stale)
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (mok[i]) {
-              const float4 o = (t.nkt == 0) ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
-              *reinterpret_cast<float4*>(ws + (long long)(4 * i) * p.N) = o;
-            }
+            stg128_if(ws + (long long)(4 * i) * Nv, empty ? 0.f : v[i][0], empty ? 0.f : v[i][1], empty ? 0.f : v[i][2],
+                      empty ? 0.f : v[i][3], mok[i]);
           continue;
         }
-        if (p.bias) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        if (feat & F_BIAS) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n));
 #pragma unroll
           for (int i = 0; i < 8; ++i) { v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w; }
         }
-        if (p.rowbias) {
+        if (feat & F_ROWBIAS) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (mok[i]) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(p.rowbias + (long long)((mbase + 4 * i) / p.rowbias_div) * p.ld_rowbias + n));
-              v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
-            }
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = ldg128_nc_if(p.rowbias + (long long)((mbase + 4 * i) / p.rowbias_div) * p.ld_rowbias + n, mok[i]);
+            v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
+          }
         }
-        if (p.out_pre) {
+        if (feat & F_PRE) {
           float* op = p.out_pre + (long long)mbase * p.ld_pre + n;
+          const long long st4 = 4 * p.ld_pre;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (mok[i]) *reinterpret_cast<float4*>(op + (long long)(4 * i) * p.ld_pre) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+          for (int i = 0; i < 8; ++i) stg128_if(op + i * st4, v[i][0], v[i][1], v[i][2], v[i][3], mok[i]);
         }
-        if (p.act != DOST_ACT_NONE) {
+        if (feat & F_ACT) {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[i][j] = (v[i][j] > 0.f) ? v[i][j] : pslope * v[i][j];
         }
-        if (p.dact_hi) {
+        if (feat & F_DACT) {
           const __nv_bfloat16* dp = p.dact_hi + (long long)mbase * p.ld_dact + n;
+          const long long st4 = 4 * p.ld_dact;
+          const float ds = p.dact_slope;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (mok[i]) {
-              const uint2 sgn = __ldg(reinterpret_cast<const uint2*>(dp + (long long)(4 * i) * p.ld_dact));
-              // bf16 value > 0  <=>  sign bit clear and magnitude bits non-zero
-              const uint32_t h[4] = {sgn.x & 0xFFFFu, sgn.x >> 16, sgn.y & 0xFFFFu, sgn.y >> 16};
+          for (int i = 0; i < 8; ++i) {
+            const uint2 sgn = ldg64_nc_if(dp + i * st4, mok[i]);
+            // bf16 value > 0  <=>  sign bit clear and magnitude bits non-zero
+            const uint32_t h[4] = {sgn.x & 0xFFFFu, sgn.x >> 16, sgn.y & 0xFFFFu, sgn.y >> 16};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) v[i][j] *= ((h[j] & 0x8000u) == 0 && (h[j] & 0x7FFFu) != 0) ? 1.f : p.dact_slope;
-            }
+            for (int j = 0; j < 4; ++j) v[i][j] *= ((h[j] & 0x8000u) == 0 && (h[j] & 0x7FFFu) != 0) ? 1.f : ds;
+          }
         }
-        if (p.residual) {
-          const float* rp = p.residual + (p.zmode == 1 ? (long long)t.z * p.res_bstride : 0) + (long long)mbase * p.ld_res + n;
+        if (feat & F_RES) {
+          const float* rp = res_v + (p.zmode == 1 ? (long long)t.z * p.res_bstride : 0) + (long long)mbase * ldres_v + n;
+          const long long st4 = 4 * ldres_v;
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (mok[i]) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(rp + (long long)(4 * i) * p.ld_res));
+          for (int i = 0; i < 8; ++i) {
+            const float4 q = ldg128_nc_if(rp + i * st4, mok[i]);
+            v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
+          }
+        }
+        if (feat & F_OUT) {
+          float* op = out_v + (p.c_rowoff ? (long long)__ldg(p.c_rowoff + t.z) * ldc_v
+                                          : (p.zmode == 1 ? (long long)t.z * p.c_bstride : 0)) + (long long)mbase * ldc_v + n;
+          const long long st4 = 4 * ldc_v;
+          if (feat & F_ACC) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 q = ldg128_if(op + i * st4, mok[i]);
               v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
             }
-        }
-        if (p.out) {
-          float* op = p.out + (p.c_rowoff ? (long long)__ldg(p.c_rowoff + t.z) * p.ldc
-                                          : (p.zmode == 1 ? (long long)t.z * p.c_bstride : 0)) + (long long)mbase * p.ldc + n;
-          if (p.accumulate) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (mok[i]) {
-                const float4 q = *reinterpret_cast<const float4*>(op + (long long)(4 * i) * p.ldc);
-                v[i][0] += q.x; v[i][1] += q.y; v[i][2] += q.z; v[i][3] += q.w;
-              }
           }
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (mok[i]) *reinterpret_cast<float4*>(op + (long long)(4 * i) * p.ldc) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+          for (int i = 0; i < 8; ++i) stg128_if(op + i * st4, v[i][0], v[i][1], v[i][2], v[i][3], mok[i]);
         }
-        if (p.out_hi) {
-          __nv_bfloat16* hp = p.out_hi + (long long)mbase * p.ld_op + n;
-          __nv_bfloat16* lp = p.out_lo ? p.out_lo + (long long)mbase * p.ld_op + n : nullptr;
+        if (feat & F_HI) {
+          __nv_bfloat16* hp = hi_v + (long long)mbase * ldop_v + n;
+          const long long st4 = 4 * ldop_v;
+          uint2 hi[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (mok[i]) {
-              uint2 hi;
-              hi.x = pack_bf16(v[i][0], v[i][1]);
-              hi.y = pack_bf16(v[i][2], v[i][3]);
-              *reinterpret_cast<uint2*>(hp + (long long)(4 * i) * p.ld_op) = hi;
-              if (lp) {
-                uint2 lo;
-                lo.x = pack_bf16(v[i][0] - __uint_as_float(hi.x << 16), v[i][1] - __uint_as_float(hi.x & 0xFFFF0000u));
-                lo.y = pack_bf16(v[i][2] - __uint_as_float(hi.y << 16), v[i][3] - __uint_as_float(hi.y & 0xFFFF0000u));
-                *reinterpret_cast<uint2*>(lp + (long long)(4 * i) * p.ld_op) = lo;
-              }
+          for (int i = 0; i < 8; ++i) {
+            hi[i].x = pack_bf16(v[i][0], v[i][1]);
+            hi[i].y = pack_bf16(v[i][2], v[i][3]);
+            stg64_if(hp + i * st4, hi[i].x, hi[i].y, mok[i]);
+          }
+          if (feat & F_LO) {
+            __nv_bfloat16* lp = lo_v + (long long)mbase * ldop_v + n;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t lx = pack_bf16(v[i][0] - __uint_as_float(hi[i].x << 16), v[i][1] - __uint_as_float(hi[i].x & 0xFFFF0000u));
+              const uint32_t ly = pack_bf16(v[i][2] - __uint_as_float(hi[i].y << 16), v[i][3] - __uint_as_float(hi[i].y & 0xFFFF0000u));
+              stg64_if(lp + i * st4, lx, ly, mok[i]);
             }
+          }
         }
-        if (p.colpart) {       // column sums of this warp's 32 rows, fixed order: the thread's 8 rows, then xor-8, xor-16
+        if (feat & F_COLPART) {       // column sums of this warp's 32 rows, fixed order: the thread's 8 rows, then xor-8, xor-16
           float cs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (mok[i]) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) cs[j] += v[i][j];
-            }
+            for (int j = 0; j < 4; ++j) cs[j] += mok[i] ? v[i][j] : 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);

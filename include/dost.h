@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 6
+#define DOST_ABI_VERSION 7
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -309,6 +309,32 @@ int dost_eval_metrics(int dtype, const void* pred, const void* y, int clamp_pred
 int dost_adamw_step(int ntensors, void* const* params, const void* const* grads, void* const* exp_avg,
                     void* const* exp_avg_sq, const long long* numel, double lr, double beta1, double beta2, double eps,
                     double weight_decay, long long step, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * On-device batch assembly from a packed crystal store.  Replaces the CPU collate of
+ * torch_geometric.loader.DataLoader / Batch.from_data_list as the launchers use it (main_eDOS.py:54-56,
+ * main_phDOS.py:52-54): node and edge tensors of the selected crystals concatenated in batch order, edge_index
+ * shifted by each crystal's node offset, batch = repeat_interleave(arange(B), n_b), per-crystal fields stacked.
+ * Store layout: crystal c owns rows node_ptr_all[c]..node_ptr_all[c+1] of every node table and rows
+ * edge_ptr_all[c]..edge_ptr_all[c+1] of every edge table; edge_index_all [2,E_all] holds crystal-LOCAL node ids.
+ * All index arrays are int64 on the device.  Bit-exact (copies and integer adds only).
+ * ------------------------------------------------------------------------------------------- */
+/* node_ptr_out[B+1], edge_ptr_out[B+1] (edge tables optional, both or neither) = exclusive scans of the selected
+ * crystals' node / edge counts; nmax_out (optional, 1 int64) = largest node count = to_dense_batch's padding length
+ * (DOSTransformer.py:61); *bad_flag is set to 1 when an id is outside [0,C) (that crystal then counts as empty). */
+int dost_collate_ptr(const int64_t* ids, long long B, const int64_t* node_ptr_all, const int64_t* edge_ptr_all,
+                     long long C, int64_t* node_ptr_out, int64_t* edge_ptr_out, int64_t* nmax_out, int32_t* bad_flag,
+                     dost_stream_t stream);
+/* Segmented row copy of one table, rows of row_bytes (multiple of 4).  Ragged table: src_ptr_all = the store's
+ * node_ptr_all or edge_ptr_all and out_ptr = the matching scan from dost_collate_ptr; per-crystal table (glob, system,
+ * targets): both NULL, row ids[b] -> row b, rows_out == B. */
+int dost_collate_rows(const void* src, const int64_t* src_ptr_all, const int64_t* ids, const int64_t* out_ptr,
+                      long long B, long long rows_out, long long row_bytes, void* dst, dost_stream_t stream);
+/* edge_index_out [2,E_out] = local ids + node_ptr_out[b]; batch_out [N_out] = b.  Either output may be NULL. */
+int dost_collate_index(const int64_t* edge_index_all, long long E_all, const int64_t* node_ptr_all,
+                       const int64_t* edge_ptr_all, const int64_t* ids, const int64_t* node_ptr_out,
+                       const int64_t* edge_ptr_out, long long B, long long N_out, long long E_out,
+                       int64_t* edge_index_out, int64_t* batch_out, dost_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -224,6 +224,31 @@ def crystal_ptr(batch: torch.Tensor, B: Optional[int] = None) -> Tuple[torch.Ten
     return torch.cat([n.new_zeros(1), n.cumsum(0)]), int(n.max())
 
 
+def collate(graphs) -> Dict[str, object]:
+    """Restatement of the PyG collate the launchers run on the CPU (torch_geometric.loader.DataLoader ->
+    Batch.from_data_list; call sites main_eDOS.py:54-56, main_phDOS.py:52-54; PyG is absent and unpinned, so this follows
+    its published semantics): tensors are concatenated along dim 0 in list order (0-d tensors are stacked),
+    ``edge_index`` along dim 1 after adding the running node offset, ``batch`` = repeat_interleave(arange(B), n),
+    ``ptr`` = node offsets, non-tensor fields become lists.  ``graphs``: mappings with crystal-local ``edge_index``."""
+    keys = list(graphs[0].keys())
+    out: Dict[str, object] = {}
+    n = torch.tensor([int(g["x"].shape[0]) for g in graphs], dtype=torch.int64)
+    ptr = torch.cat([n.new_zeros(1), n.cumsum(0)])
+    for k in keys:
+        vals = [g[k] for g in graphs]
+        if not torch.is_tensor(vals[0]):
+            out[k] = list(vals)
+        elif k == "edge_index":
+            out[k] = torch.cat([v + ptr[i] for i, v in enumerate(vals)], dim=1)
+        elif vals[0].dim() == 0:
+            out[k] = torch.stack(vals)
+        else:
+            out[k] = torch.cat(vals, dim=0)
+    out["batch"] = torch.repeat_interleave(torch.arange(len(graphs), dtype=torch.int64), n)
+    out["ptr"] = ptr
+    return out
+
+
 def state_dict_of(module: torch.nn.Module, dtype=None) -> Dict[str, torch.Tensor]:
     sd = {k: v.detach().clone() for k, v in module.state_dict().items()}
     if dtype is not None:

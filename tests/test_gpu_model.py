@@ -296,3 +296,55 @@ def _concat(gs):
     return CrystalBatch(x=torch.cat(xs), edge_index=torch.cat(eis, 1), edge_attr=torch.cat(eas), glob=torch.cat([g.glob for g in gs]),
                         batch=torch.cat(bs), system=torch.cat([g.system for g in gs]), y_ft=torch.cat([g.y_ft for g in gs]),
                         mp_id=sum([g.mp_id for g in gs], []), max_num_nodes=max(g.max_num_nodes for g in gs))
+
+
+# ---------------------------------------------------------------------------------------------- on-device collate (8f-3)
+@pytest.mark.parametrize("kind", ["edos", "phonon"])
+def test_device_collate_bit_exact(kind):
+    """PackedCrystals.collate == oracle.collate (PyG semantics) on every field, bit for bit: shuffled ids, repeats,
+    single crystal, empty batch; and the model's outputs on the device-assembled batch equal those on the host one."""
+    from dostransformer_b200.collate import PackedCrystals, split_batch
+    src = make_edos_batch(37, seed=31) if kind == "edos" else make_phonon_batch(23, seed=32)
+    graphs = split_batch(src)
+    gd = [{k: g[k] for k in g.keys()} for g in graphs]
+    pk = PackedCrystals.from_graphs(graphs, device=DEV)
+    gen = torch.Generator().manual_seed(5)
+    C = len(graphs)
+    cases = [torch.arange(C), torch.randperm(C, generator=gen), torch.randint(0, C, (50,), generator=gen),
+             torch.tensor([C - 1]), torch.tensor([3, 3, 3, 0]), torch.zeros(0, dtype=torch.int64)]
+    for ids in cases:
+        got = pk.collate(ids)
+        if ids.numel() == 0:
+            assert got.x.shape[0] == 0 and got.batch.numel() == 0 and got.edge_index.shape == (2, 0)
+            assert got.ptr.tolist() == [0]
+            continue
+        want = O.collate([gd[i] for i in ids.tolist()])
+        assert set(want) <= set(got.keys())
+        for k, v in want.items():
+            if torch.is_tensor(v):
+                g = got[k]
+                assert g.is_cuda and g.dtype == v.dtype and g.shape == v.shape, (k, g.shape, v.shape)
+                assert torch.equal(g.cpu(), v), k
+            else:
+                assert got[k] == v, k
+        assert got.max_num_nodes == int(torch.bincount(want["batch"]).max())
+    with pytest.raises(IndexError):
+        pk.collate([0, C])
+    # the assembled batch drives the model exactly like the host-collated one
+    ids = torch.randperm(C, generator=gen)[:8]
+    host = O.collate([gd[i] for i in ids.tolist()])
+    from dostransformer_b200.synthetic import CrystalBatch
+    hb = CrystalBatch(**{k: v for k, v in host.items() if k != "ptr"}).to(DEV)
+    hb["max_num_nodes"] = int(torch.bincount(host["batch"]).max())   # same padding metadata -> same attention kernels
+    torch.manual_seed(0)
+    if kind == "edos":
+        model = DOSTransformer(2, 1, 200, 41, 2, 128, torch.device(DEV), 0.0).to(DEV)
+    else:
+        torch.set_default_dtype(torch.float64)
+        model = DOSTransformer_phonon(2, 1, 118, 4, 64, torch.device(DEV), 0.0).to(DEV)
+    model.eval()
+    with torch.no_grad():
+        a = model(pk.collate(ids))
+        b = model(hb)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)

@@ -113,7 +113,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/dost.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.dost_abi_version() == 6
+    assert lib.dost_abi_version() == 7
     # argument validation works without a GPU (no launch happens)
     assert lib.dost_gemm(None, None, 0, None) == -1
     assert b"null descriptor" in lib.dost_last_error()
@@ -141,3 +141,31 @@ def test_fused_adamw_interface_mirrors_torch():
     opt.zero_grad()
     with pytest.raises(ValueError):
         AdamW([])
+
+
+def test_oracle_collate_inverts_split_batch():
+    """Integer / byte work of the batch assembly, host side: oracle.collate(split_batch(b)) == b bit for bit, and the
+    packed store's metadata (table kinds, counts) on a CPU-resident store."""
+    from dostransformer_b200.collate import PackedCrystals, split_batch
+    from oracle.dost_oracle import collate
+    for b in (make_edos_batch(9, seed=21), make_phonon_batch(6, seed=22)):
+        graphs = split_batch(b)
+        c = collate([{k: g[k] for k in g.keys()} for g in graphs])
+        for k in b.keys():
+            if k == "max_num_nodes":
+                continue
+            if torch.is_tensor(b[k]):
+                assert c[k].dtype == b[k].dtype and torch.equal(c[k], b[k]), k
+            else:
+                assert c[k] == b[k], k
+        n = torch.bincount(b.batch)
+        assert torch.equal(c["ptr"], torch.cat([n.new_zeros(1), n.cumsum(0)]))
+        pk = PackedCrystals.from_graphs(graphs, device="cpu")
+        assert len(pk) == b.num_graphs and pk.kinds["x"] == "node" and pk.kinds["system"] == "crystal"
+        assert pk.kinds["edge_attr" if "edge_attr" in b else "edge_vec"] == "edge"
+        assert int(pk.node_count.sum()) == b.x.shape[0] and int(pk.edge_count.sum()) == b.edge_index.shape[1]
+        assert int(pk.edge_index.min()) == 0 and int(pk.edge_index.max()) == int(n.max()) - 1 - ("glob" in b)
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            if torch.cuda.is_available():
+                raise RuntimeError("no CPU fallback")      # GPU box: the CPU-resident store is rejected below instead
+            pk.collate([0, 1])
