@@ -470,6 +470,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
       tmem_ld32(taddr0, r);
 #pragma unroll 1
       for (int c0 = 0; c0 < CH; c0 += 32) {
+        const int n = nbase + c0;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);       // requested before the staging round trip, which hides its latency
+        if ((feat & F_BIAS) && n < Nv) b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n));
         tmem_ld_wait();
         // ---- stage: lane = accumulator row; 16-byte chunk j goes to column chunk j ^ (row & 7) (conflict-free)
 #pragma unroll
@@ -494,7 +497,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
         }
         __syncwarp();                                      // staging tile may be overwritten by the next chunk
-        const int n = nbase + c0;
         if (n >= Nv || t.m0 + quad * 32 >= Mv) continue;    // N % 4 == 0: a thread's 4 columns are all in or all out
         bool mok[8];
         const int mlim = (feat & F_ROWLIM) ? min(Mv, __ldg(p.c_rowlim + t.z)) : Mv;
@@ -510,7 +512,6 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           continue;
         }
         if (feat & F_BIAS) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n));
 #pragma unroll
           for (int i = 0; i < 8; ++i) { v[i][0] += b4.x; v[i][1] += b4.y; v[i][2] += b4.z; v[i][3] += b4.w; }
         }

@@ -26,17 +26,24 @@ def timeit(fn, reps=6):
     return e0.elapsed_time(e1) / reps
 
 
+ONE = (int(sys.argv[2]), sys.argv[3]) if len(sys.argv) > 3 and sys.argv[1] == "--one" else None   # --one <K> <fp32|planes|hi>
 out = torch.empty(M, N, device=dev)
 op = ops.empty_planes(M, N, dev, True)
 oph = ops.empty_planes(M, N, dev, False)
 bias = torch.randn(N, device=dev)
 with ops.precision("bf16x3"):
-    for K in (64, 128, 256, 512, 1024):
+    for K in ((ONE[0],) if ONE else (64, 128, 256, 512, 1024)):
         a, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev)
         ap, bp = ops.split_planes(a), ops.split_planes(b)
         base = dict(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=bp, b_mode=L.KC)
         variants = {"fp32 out": dict(out=out), "planes hi+lo, bias+relu": dict(out_planes=op, bias=bias, act=L.ACT_RELU),
                     "hi plane only": dict(out_planes=oph)}
+        if ONE:
+            key = {"fp32": "fp32 out", "planes": "planes hi+lo, bias+relu", "hi": "hi plane only"}[ONE[1]]
+            for _ in range(4):
+                ops.gemm_planes(**base, **variants[key])
+            torch.cuda.synchronize()
+            sys.exit(0)
         for name, kw in variants.items():
             ms = timeit(lambda: ops.gemm_planes(**base, **kw))
             print(f"N={N} K={K:5d} {name:26s} {ms:7.3f} ms  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s (x3 effective)", flush=True)
