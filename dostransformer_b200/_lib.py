@@ -12,7 +12,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdost_b200.so")
+# DOST_B200_LIB: an alternative build of the same library (A/B timing of kernel variants on one box)
+LIB_PATH = os.environ.get("DOST_B200_LIB") or os.path.join(_HERE, "libdost_b200.so")
 
 F32, F64 = 0, 1
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_PRELU = 0, 1, 2, 3

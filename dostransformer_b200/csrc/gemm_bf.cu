@@ -473,6 +473,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         const int n = nbase + c0;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);       // requested before the staging round trip, which hides its latency
         if ((feat & F_BIAS) && n < Nv) b4 = __ldg(reinterpret_cast<const float4*>(bias_v + n));
+        uint2 sgn[8];
+        if (feat & F_DACT) {                               // activation-derivative mask, also requested early
+          const int mlim0 = (feat & F_ROWLIM) ? min(Mv, __ldg(p.c_rowlim + t.z)) : Mv;
+          const __nv_bfloat16* dp = p.dact_hi + (long long)mbase * p.ld_dact + n;
+          const long long st4 = 4 * p.ld_dact;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sgn[i] = ldg64_nc_if(dp + i * st4, mbase + 4 * i < mlim0 && n < Nv);
+        }
         tmem_ld_wait();
         // ---- stage: lane = accumulator row; 16-byte chunk j goes to column chunk j ^ (row & 7) (conflict-free)
 #pragma unroll
@@ -535,16 +543,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             for (int j = 0; j < 4; ++j) v[i][j] = (v[i][j] > 0.f) ? v[i][j] : pslope * v[i][j];
         }
         if (feat & F_DACT) {
-          const __nv_bfloat16* dp = p.dact_hi + (long long)mbase * p.ld_dact + n;
-          const long long st4 = 4 * p.ld_dact;
           const float ds = p.dact_slope;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const uint2 sgn = ldg64_nc_if(dp + i * st4, mok[i]);
-            // bf16 value > 0  <=>  sign bit clear and magnitude bits non-zero
-            const uint32_t h[4] = {sgn.x & 0xFFFFu, sgn.x >> 16, sgn.y & 0xFFFFu, sgn.y >> 16};
+            // the bf16 bit pattern, moved to the top half of a word, is the same number as an fp32: compare that with 0
+            // (-0 and +0 take the slope like every non-positive input; the masks come from activations, never NaN)
+            const float m[4] = {__uint_as_float(sgn[i].x << 16), __uint_as_float(sgn[i].x & 0xFFFF0000u),
+                                __uint_as_float(sgn[i].y << 16), __uint_as_float(sgn[i].y & 0xFFFF0000u)};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) v[i][j] *= ((h[j] & 0x8000u) == 0 && (h[j] & 0x7FFFu) != 0) ? 1.f : ds;
+            for (int j = 0; j < 4; ++j) v[i][j] = (m[j] > 0.f) ? v[i][j] : ds * v[i][j];
           }
         }
         if (feat & F_RES) {
@@ -595,7 +602,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
 #pragma unroll
           for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) cs[j] += mok[i] ? v[i][j] : 0.f;
+            for (int j = 0; j < 4; ++j) cs[j] += mok[i] ? v[i][j] : 0.f;     // rows past M / the ragged limit do not count
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
@@ -724,20 +731,30 @@ __global__ void __launch_bounds__(256) split_planes_colsum_kernel(const float* _
   }
 }
 
-// 32 columns x 8 lanes per block: lane ry sums chunks ry, ry + 8, ...; lanes combined in order (deterministic)
-__global__ void __launch_bounds__(256) colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out) {
-  __shared__ float sm[8][33];
+// 32 columns x 32 row lanes per block: lane ry sums chunks ry, ry + 32, ... (four independent loads in flight), lanes are
+// combined in order (deterministic).  Only ceil(W / 32) blocks exist, so each keeps as many loads in flight as it can.
+__global__ void __launch_bounds__(1024) colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out) {
+  __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
-  float s = 0.f;
-  if (c < W)
-    for (int b = ry; b < nchunks; b += 8) s += ws[(long long)b * W + c];
-  sm[ry][cx] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (c < W) {
+    const float* src = ws + c;
+    int b = ry;
+    for (; b + 96 < nchunks; b += 128) {
+      s0 += src[(long long)b * W];
+      s1 += src[(long long)(b + 32) * W];
+      s2 += src[(long long)(b + 64) * W];
+      s3 += src[(long long)(b + 96) * W];
+    }
+    for (; b < nchunks; b += 32) s0 += src[(long long)b * W];
+  }
+  sm[ry][cx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
   if (ry == 0 && c < W) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][cx];
+    for (int k = 0; k < 32; ++k) t += sm[k][cx];
     out[c] = t;
   }
 }
@@ -1003,7 +1020,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   }
   if (rc != DOST_OK) return rc;
   if (h->colsum) {
-    colsum_stage2_kernel<<<ceil_div(h->N, 32), 256, 0, st>>>(p.colpart, nrb, h->N, h->colsum);
+    colsum_stage2_kernel<<<ceil_div(h->N, 32), 1024, 0, st>>>(p.colpart, nrb, h->N, h->colsum);
     rc = check_launch("gemm_bf16 column sums");
     if (rc != DOST_OK) return rc;
   }
@@ -1055,7 +1072,7 @@ extern "C" int dost_split_planes_colsum(const float* x, long long ld, long long 
                                                              rpc, (float*)workspace);
   int rc = dost::check_launch("split_planes_colsum");
   if (rc != DOST_OK) return rc;
-  dost::bf::colsum_stage2_kernel<<<dost::ceil_div(cols, 32), 256, 0, st>>>((const float*)workspace, nch, cols, colsum);
+  dost::bf::colsum_stage2_kernel<<<dost::ceil_div(cols, 32), 1024, 0, st>>>((const float*)workspace, nch, cols, colsum);
   return dost::check_launch("split_planes_colsum stage2");
 }
 

@@ -31,13 +31,18 @@ out = torch.empty(M, N, device=dev)
 op = ops.empty_planes(M, N, dev, True)
 oph = ops.empty_planes(M, N, dev, False)
 bias = torch.randn(N, device=dev)
+mask = ops.split_planes(torch.randn(M, N, device=dev))
+csum = torch.empty(N, device=dev)
 with ops.precision("bf16x3"):
     for K in ((ONE[0],) if ONE else (64, 128, 256, 512, 1024)):
         a, b = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev)
         ap, bp = ops.split_planes(a), ops.split_planes(b)
         base = dict(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=bp, b_mode=L.KC)
         variants = {"fp32 out": dict(out=out), "planes hi+lo, bias+relu": dict(out_planes=op, bias=bias, act=L.ACT_RELU),
-                    "hi plane only": dict(out_planes=oph)}
+                    "hi plane only": dict(out_planes=oph),
+                    "planes, dact+colsum (fc2 dA)": dict(out_planes=op, dact=mask, dact_slope=0.0, colsum_out=csum),
+                    "planes, dact": dict(out_planes=op, dact=mask, dact_slope=0.0),
+                    "planes, colsum": dict(out_planes=op, colsum_out=csum)}
         if ONE:
             key = {"fp32": "fp32 out", "planes": "planes hi+lo, bias+relu", "hi": "hi plane only"}[ONE[1]]
             for _ in range(4):
@@ -46,7 +51,7 @@ with ops.precision("bf16x3"):
             sys.exit(0)
         for name, kw in variants.items():
             ms = timeit(lambda: ops.gemm_planes(**base, **kw))
-            print(f"N={N} K={K:5d} {name:26s} {ms:7.3f} ms  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s (x3 effective)", flush=True)
+            print(f"N={N} K={K:5d} {name:30s} {ms:7.3f} ms  {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s (x3 effective)", flush=True)
     # the same output volume as 4 column tiles of N=256 (K=256): tile count unchanged, B operand 4x smaller
     K = 256
     a, b = torch.randn(M, K, device=dev), torch.randn(256, K, device=dev)
