@@ -155,6 +155,15 @@ _SIGNATURES = {
                                     C.c_longlong, C.c_void_p, C.c_void_p]),
     "dost_collate_index": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_longlong, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dost_neighbor_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_int,
+                                      C.c_void_p, C.c_void_p]),
+    "dost_neighbor_fill": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_double, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "dost_knn_select": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_longlong, C.c_double,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dost_gaussian_expand": (C.c_int, [C.c_void_p, C.c_longlong, C.c_double, C.c_double, C.c_int, C.c_double, C.c_void_p,
+                                       C.c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -173,7 +182,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 7:
+    if lib.dost_abi_version() != 8:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 7
+#define DOST_ABI_VERSION 8
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -335,6 +335,34 @@ int dost_collate_index(const int64_t* edge_index_all, long long E_all, const int
                        const int64_t* edge_ptr_all, const int64_t* ids, const int64_t* node_ptr_out,
                        const int64_t* edge_ptr_out, long long B, long long N_out, long long E_out,
                        int64_t* edge_index_out, int64_t* batch_out, dost_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Periodic neighbour lists and eDOS bond features on the device.  Replaces the reference's offline
+ * CPU graph construction: ase.neighbor_list("ijS", cutoff, self_interaction=True) + edge vectors (utils.py:267-273) and
+ * pymatgen get_all_neighbors(8.0) -> 12 nearest -> Gaussian expansion (data/mat2graph.py:162-179,185,212-243).
+ * lattice [C,9] fp64 (rows = lattice vectors), pos [N,3] fp64 Cartesian, node_ptr [C+1], crystal_of [N] (= batch), int64.
+ * Canonical edge order: (centre i, neighbour j, shift Sx, Sy, Sz) ascending.  Arithmetic contract (each op rounded, no
+ * FMA): s = (Sx*L0 + Sy*L1) + Sz*L2; v = (pos[j] - pos[i]) + s; d = sqrt((vx*vx + vy*vy) + vz*vz); neighbour iff d < cutoff;
+ * the zero-shift self pair only with self_interaction.  Two passes: count [N], exclusive scan by the caller, fill.
+ * ------------------------------------------------------------------------------------------- */
+int dost_neighbor_count(const double* lattice, const double* pos, const int64_t* node_ptr, const int64_t* crystal_of,
+                        long long N, double cutoff, int self_interaction, int64_t* count, dost_stream_t stream);
+/* edge_ptr [N+1] = exclusive scan of count.  edge_src/edge_dst [E] (crystal-local ids if local_ids, else row ids of pos),
+ * optional edge_shift [E,3] int64, edge_vec [E,3], edge_len [E]. */
+int dost_neighbor_fill(const double* lattice, const double* pos, const int64_t* node_ptr, const int64_t* crystal_of,
+                       long long N, double cutoff, int self_interaction, const int64_t* edge_ptr, int local_ids,
+                       int64_t* edge_src, int64_t* edge_dst, int64_t* edge_shift, double* edge_vec, double* edge_len,
+                       dost_stream_t stream);
+/* The k nearest entries of every atom's list (stable: ties keep list order): out_idx [N,k] = edge_dst of the pick,
+ * out_dist [N,k], optional out_edge [N,k] = its edge id; short lists are padded with (pad_idx, pad_dist, -1)
+ * (mat2graph.py:223-229 pads with index 0 and distance radius + 1). */
+int dost_knn_select(const int64_t* edge_ptr, const int64_t* edge_dst, const double* edge_len, long long N, int k,
+                    long long pad_idx, double pad_dist, int64_t* out_idx, double* out_dist, int64_t* out_edge,
+                    dost_stream_t stream);
+/* GaussianDistance.expand (mat2graph.py:162-179): out [n,nfilt] fp32 = exp(-(d - mu_f)^2 / var^2), mu_f = dmin + f*step, in
+ * fp64 then rounded to fp32 like torch.Tensor(numpy_array) does. */
+int dost_gaussian_expand(const double* dist, long long n, double dmin, double step, int nfilt, double var, float* out,
+                         dost_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -161,3 +161,41 @@ def test_losses():
     ph = torch.rand(B, T)
     ref = ((ph - pg) ** 2).mean().sqrt() + ((ph - ps) ** 2).mean().sqrt()
     assert abs(O.phonon_loss(pg, ps, ph, 1.0) - ref) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------- graph construction oracle
+def test_neighbor_oracle_known_lattices():
+    """The brute-force neighbour oracle on lattices with textbook answers (the reference has no fixtures for its
+    third-party neighbour finders: parity unpinned, see oracle/neighbors_oracle.py)."""
+    import numpy as np
+    from oracle import neighbors_oracle as NO
+    # simple cubic, a = 3: 6 first neighbours at 3, 12 second at 3*sqrt(2); with self-interaction also the atom itself
+    L = np.eye(3) * 3.0
+    pos = np.zeros((1, 3))
+    nl = NO.neighbor_list(L, pos, 3.5, self_interaction=True)
+    assert len(nl["dist"]) == 7 and np.count_nonzero(nl["dist"] == 0.0) == 1 and np.count_nonzero(nl["dist"] == 3.0) == 6
+    assert (nl["shift"][nl["dist"] == 0.0] == 0).all()
+    nl = NO.neighbor_list(L, pos, 4.5, self_interaction=False)
+    assert len(nl["dist"]) == 18 and np.allclose(np.sort(nl["dist"])[6:], 3.0 * np.sqrt(2.0))
+    # canonical order: shifts ascend lexicographically for the single (i, j) pair
+    key = nl["shift"][:, 0] * 100 + nl["shift"][:, 1] * 10 + nl["shift"][:, 2]
+    assert (np.diff(key) > 0).all()
+    assert np.array_equal(nl["vec"], nl["shift"].astype(np.float64) * 3.0)
+    # fcc (conventional cell, 4 atoms, a = 4): 12 nearest neighbours at a / sqrt(2) for every atom
+    Lf = np.eye(3) * 4.0
+    pf = np.array([[0, 0, 0], [0, 2, 2], [2, 0, 2], [2, 2, 0]], dtype=np.float64)
+    bonds, feats = NO.edos_edges(Lf, pf, radius=8.0, k=12)
+    assert bonds.shape == (48, 2) and feats.shape == (48, 41) and feats.dtype == np.float32
+    nlf = NO.neighbor_list(Lf, pf, 8.0, self_interaction=False)
+    idx, dist = NO.knn_from_list(nlf, 4, 12, 8.0)
+    assert np.allclose(dist, 4.0 / np.sqrt(2.0)) and (bonds[:, 0] == np.repeat(np.arange(4), 12)).all()
+    # the Gaussian filter peaks at the centre closest to the distance (2.828 -> centre 14 = 2.8)
+    assert (feats.argmax(axis=1) == 14).all()
+    # a sparse cell: fewer than 12 images within the radius -> padded with index 0 / distance radius + 1
+    Ls = np.eye(3) * 7.5
+    bonds, feats = NO.edos_edges(Ls, np.array([[0.0, 0.0, 0.0], [3.0, 0.0, 0.0]]), radius=8.0, k=12)
+    nls = NO.neighbor_list(Ls, np.array([[0.0, 0.0, 0.0], [3.0, 0.0, 0.0]]), 8.0, self_interaction=False)
+    per_atom = np.bincount(nls["src"], minlength=2)
+    assert (per_atom < 12).all()
+    idx, dist = NO.knn_from_list(nls, 2, 12, 8.0)
+    assert (dist[0, per_atom[0]:] == 9.0).all() and (idx[0, per_atom[0]:] == 0).all() and (np.diff(dist, axis=1) >= 0).all()
