@@ -103,3 +103,29 @@ def edos_edges(lattice, pos, node_ptr, radius: float = 8.0, k: int = 12) -> Dict
     feats = gaussian_expand(dist, 0.0, radius, 0.2)
     return {"edge_index": torch.stack([centre, nbr]), "edge_attr": feats.reshape(N * k, -1), "nbr_dist": dist,
             "nbr_idx_local": idx}
+
+
+def edos_graph_batch(lattice, pos, node_ptr, atom_feats: torch.Tensor, radius: float = 8.0, k: int = 12, **per_crystal):
+    """Structures -> the eDOS model's input batch, on the device: what ``get_crystal_graph`` (mat2graph.py:120-159) builds
+    per crystal and PyG then collates.  ``atom_feats`` [N,F] are the (already scaled) element feature rows of the atoms; every
+    crystal gets the all-zero prompt node appended after its atoms (mat2graph.py:155-158), which has no bonds; bonds are the
+    k nearest images within ``radius`` with their Gaussian distance features.  ``per_crystal`` tensors (``glob`` [2C],
+    ``system`` [C], ``y_ft`` [C*T] ...) are passed through."""
+    from .synthetic import CrystalBatch
+    e = edos_edges(lattice, pos, node_ptr, radius, k)
+    dev = pos.device
+    node_ptr = node_ptr.to(device=dev, dtype=torch.int64)
+    C = node_ptr.numel() - 1
+    N = pos.shape[0]
+    counts = node_ptr[1:] - node_ptr[:-1]
+    crystal_of = torch.repeat_interleave(torch.arange(C, device=dev, dtype=torch.int64), counts, output_size=N)
+    x = torch.zeros(N + C, atom_feats.shape[1], dtype=atom_feats.dtype, device=dev)
+    rows = torch.arange(N, device=dev, dtype=torch.int64) + crystal_of        # one prompt node per preceding crystal
+    x[rows] = atom_feats.to(dev)
+    ei = e["edge_index"]
+    edge_index = torch.stack([ei[0] + crystal_of[ei[0]], ei[1] + crystal_of[ei[1]]])
+    batch = torch.repeat_interleave(torch.arange(C, device=dev, dtype=torch.int64), counts + 1, output_size=N + C)
+    # one host read for the padding length; this is the offline stage (the training loop gets it from the packed store)
+    nmax = int(counts.max().item()) + 1 if C else 0
+    return CrystalBatch(x=x, edge_index=edge_index, edge_attr=e["edge_attr"], batch=batch, max_num_nodes=nmax,
+                        **per_crystal)

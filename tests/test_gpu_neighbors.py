@@ -89,3 +89,39 @@ def test_edos_edges_padding_and_empty():
     # an empty batch is a no-op
     e = NB.neighbor_list(lattice[:0], pos[:0], torch.zeros(1, dtype=torch.int64, device=DEV), 4.0)
     assert e["edge_index"].shape == (2, 0) and e["edge_ptr"].tolist() == [0]
+
+
+def test_edos_graph_batch_feeds_the_model():
+    """Structures -> graph -> model on the device, against the oracle's per-crystal construction + PyG-style collate."""
+    from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+    from oracle import dost_oracle as O
+    sizes = [3, 7, 1, 12]
+    cells, lattice, pos, node_ptr = _batch(13, sizes, 3.5, 6.0)
+    gen = torch.Generator().manual_seed(3)
+    feats = torch.randn(sum(sizes), 200, generator=gen)
+    C = len(sizes)
+    glob = torch.randn(2 * C, generator=gen)
+    system = torch.randint(0, 7, (C,), generator=gen)
+    got = NB.edos_graph_batch(lattice, pos, node_ptr, feats.to(DEV), glob=glob.to(DEV), system=system.to(DEV))
+    graphs, off = [], 0
+    for b, ((L, p), n) in enumerate(zip(cells, sizes)):
+        bonds, bf = NO.edos_edges(L, p)
+        graphs.append({"x": torch.cat([feats[off:off + n], torch.zeros(1, 200)]), "edge_index": torch.tensor(bonds.T),
+                       "edge_attr": torch.tensor(bf), "glob": glob[2 * b:2 * b + 2], "system": system[b]})
+        off += n
+    want = O.collate(graphs)
+    for k in ("x", "edge_index", "batch", "glob", "system"):
+        assert torch.equal(got[k].cpu(), want[k]), k
+    assert (got["edge_attr"].cpu().view(torch.int32) - want["edge_attr"].view(torch.int32)).abs().max() <= 1
+    assert got.max_num_nodes == max(sizes) + 1
+    torch.manual_seed(0)
+    model = DOSTransformer(2, 1, 200, 41, 2, 128, torch.device(DEV), 0.0).to(DEV).eval()
+    with torch.no_grad():
+        dg, x, ds = model(got)
+    assert dg.shape == (C, 201) and ds.shape == (C, 201) and x.shape == (sum(sizes) + C, 128)
+    assert bool(torch.isfinite(dg).all()) and bool(torch.isfinite(ds).all())
+    # same numbers as the CPU oracle of the model on the oracle-built batch (fp32 tolerance of the model tests)
+    sd = O.state_dict_of(model.cpu())
+    from dostransformer_b200.synthetic import CrystalBatch
+    ref = O.edos_forward(sd, CrystalBatch(**{k: v for k, v in want.items() if k != "ptr"}))
+    assert (dg.cpu() - ref[0]).abs().max() <= 1e-4 * ref[0].abs().max()
