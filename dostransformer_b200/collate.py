@@ -111,6 +111,21 @@ class PackedCrystals:
         output into a dataset."""
         return cls.from_graphs(split_batch(batch), device)
 
+    def shard_ids(self, ids, world: int, T: int, hidden: int = 256):
+        """Data parallel: split the global batch ``ids`` into ``world`` length-balanced parts with equal crystal counts
+        (+-1) (dp.shard_crystals on the host copy of the counts).  Returns (parts, nmax, weights): each rank collates
+        ``parts[rank]``, sets ``model.max_num_nodes = nmax`` (the global to_dense_batch padding length) and scales its
+        loss by ``weights[rank]`` so that the SUM-reduced gradients equal the single-process ones."""
+        from . import dp
+        ids_t = torch.as_tensor(ids, dtype=torch.int64).cpu()
+        ids_np = ids_t.numpy()
+        cost = dp.crystal_cost(torch.from_numpy(self.node_count[ids_np]), torch.from_numpy(self.edge_count[ids_np]), T, hidden)
+        bins = dp.shard_crystals(cost.tolist(), world)
+        parts = [ids_t[torch.as_tensor(b, dtype=torch.int64)] for b in bins]
+        nmax = int(self.node_count[ids_np].max()) if ids_np.size else 0
+        weights = [dp.loss_weight(len(b), len(ids_np)) for b in bins]
+        return parts, nmax, weights
+
     # ------------------------------------------------------------------ the hot call
     def collate(self, ids) -> CrystalBatch:
         """Assemble the batch of crystals ``ids`` (sequence / CPU int64 tensor, any order, repeats allowed) on the device."""

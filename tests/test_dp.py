@@ -95,3 +95,26 @@ def test_two_rank_gradients_equal_single_process(tmp_path):
     assert live == set(ref)                                   # the bucketed set is exactly the live set
     for k, r in ref.items():
         assert relerr(grads[k], r) < 2e-4, k
+
+
+def test_packed_store_shards_ids_like_shard_batch():
+    """PackedCrystals.shard_ids (host metadata only) gives the same partition, padding length and loss weights as
+    dp.shard_batch on the collated batch of the same crystals."""
+    from dostransformer_b200.collate import PackedCrystals, split_batch
+    g = make_edos_batch(23, seed=77)
+    store = PackedCrystals.from_graphs(split_batch(g), device="cpu")
+    ids = torch.arange(23)
+    for world in (2, 3, 8):
+        parts, nmax, weights = store.shard_ids(ids, world, T=201)
+        ref_parts, ref_nmax, ref_w, _ = dp.shard_batch(g, world, T=201)
+        assert nmax == ref_nmax and weights == pytest.approx(ref_w)
+        assert sorted(torch.cat(parts).tolist()) == ids.tolist()
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+        for p, r in zip(parts, ref_parts):
+            assert int(store.node_count[p.numpy()].sum()) == r.batch.numel()
+            assert int(store.edge_count[p.numpy()].sum()) == r.edge_index.shape[1]
+    # a shuffled subset: ids keep their identity through the partition
+    sub = torch.tensor([5, 19, 2, 11, 7])
+    parts, nmax, weights = store.shard_ids(sub, 2, T=201)
+    assert sorted(torch.cat(parts).tolist()) == sorted(sub.tolist()) and abs(sum(weights) - 1.0) < 1e-12
+    assert nmax == int(store.node_count[sub.numpy()].max())
