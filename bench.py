@@ -50,18 +50,20 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms.  The process is started BEFORE the warm-up steps: its
+    NVML attach takes 0.1-2 s (longer on an 8-GPU box) and stalls CUDA work on the box while it lasts, which must not land
+    inside the timed region; only the samples stamped inside the region (`mark()` .. `stop()`) are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.lines, self.proc = gpu_index, [], None
+        self.idx, self.lines, self.proc, self.t0 = gpu_index, [], None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -70,12 +72,23 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def wait_ready(self, timeout: float = 8.0):
+        """Blocks until the first sample has arrived (the NVML attach is over) or the timeout passes."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.lines and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.02)
+
+    def mark(self):
+        """The timed region starts now."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        t1 = time.time()
+        time.sleep(0.15)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -83,7 +96,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t0 if self.t0 is not None else 0.0
+        inside = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.12]
+        if not inside and self.lines:                    # region shorter than one sampling period: the closest sample
+            inside = [min(self.lines, key=lambda x: abs(x[0] - t1))[1]]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -316,20 +333,27 @@ def run_product(args, rank: int, world: int, local_rank: int):
         torch.cuda.synchronize()
 
     # ---------------------------------------------------------------- device-resident timing
-    for i in range(args.warmup):
-        step(resident[i % NB])
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for i in range(args.warmup):
+        step(resident[i % NB])
+    barrier()
+    if rank == 0:
+        sampler.wait_ready()     # a slow NVML attach must finish outside the timed region
+    barrier()
+    sampler.mark()
     st = torch.cuda.current_stream()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = L.launch_count()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record(st)
     for i in range(args.steps):
         step(resident[i % NB])
+        marks[i].record(st)
     e1.record(st)
     barrier()
+    dev_each = [round(a.elapsed_time(b), 2) for a, b in zip([e0] + marks[:-1], marks)]
     launches = L.launch_count() - l0
     sec = e0.elapsed_time(e1) * 1e-3
     clocks = sampler.stop() if rank == 0 else None
@@ -381,7 +405,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
                    "global_batch": B * world, "parallelism": f"dp{world}", "mean_nodes_per_batch": n_nodes,
                    "mean_edges_per_batch": n_edges, "nmax": nmax, "precision": PREC_DESC[args.precision],
                    "l2_policy": "3 distinct batches rotated; per-step activations (>1 GB) exceed the 126 MB L2"},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "ms_each_step_device": dev_each,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_sec / args.steps * 1e3, "ms_each_step": [round(x, 2) for x in per_step],
                 "api": "DOSTransformer(batch) + ops.dos_loss + loss.backward(), batch copied from pinned host memory, "
