@@ -169,3 +169,33 @@ def test_oracle_collate_inverts_split_batch():
             if torch.cuda.is_available():
                 raise RuntimeError("no CPU fallback")      # GPU box: the CPU-resident store is rejected below instead
             pk.collate([0, 1])
+
+
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/dost.h must compile as C (it is the FFI contract) and every descriptor struct must have the layout the
+    ctypes mirror in _lib.py assumes: size and the offset of every field, taken from gcc."""
+    import ctypes
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = {"dost_seg_t": _lib.Seg, "dost_gemm_t": _lib.Gemm, "dost_planes_t": _lib.PlanesC, "dost_gemm_bf16_t": _lib.GemmBf16}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "dost.h")}"',
+             'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-o", str(exe), str(src)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {(a, b): int(c) for a, b, c in (ln.split() for ln in out.strip().splitlines())}
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    # and nothing in the C struct is missing from the mirror: equal size + equal last-field offset covers trailing fields
