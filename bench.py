@@ -452,7 +452,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
         torch.manual_seed(0)     # the optimizer steps above moved the weights; nothing below depends on their values
     if world == 1:
         try:
-            line["device_collate"] = device_collate_bench(host, dev, B, step, args.steps)
+            line["device_collate"] = device_collate_bench(host, dev, B, step, args.steps, model)
         except Exception as ex:
             line["device_collate"] = {"error": repr(ex)}
     if world == 1 and args.precision == "bf16x3" and not args.no_alt:
@@ -488,7 +488,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
-def device_collate_bench(host, dev, B, step, steps):
+def device_collate_bench(host, dev, B, step, steps, model):
     """the batches' crystals packed once into HBM-resident tables; a step sends B crystal ids and the batch is
     assembled on the device (csrc/collate.cu).  Reports the assembly alone (CUDA events, bytes = read + written) and the
     end-to-end step that starts from host ids."""
@@ -519,7 +519,21 @@ def device_collate_bench(host, dev, B, step, steps):
         step(g).item()
     torch.cuda.synchronize()
     sec = time.perf_counter() - t0
+    # BASELINE configs[4] shape at store size: forward-only sweep over every crystal of the store, batches assembled on the
+    # device in length-sorted order, per-crystal evaluation, predictions kept on the device
+    from dostransformer_b200.evaluate import sweep
+    sweep(model, pk, batch_size=B)
+    torch.cuda.synchronize()
+    reps_s = 4
+    ts = time.perf_counter()
+    for _ in range(reps_s):
+        ids_s, ds_s, _ = sweep(model, pk, batch_size=B)
+    torch.cuda.synchronize()
+    sweep_sec = (time.perf_counter() - ts) / reps_s
     return {"value": B * steps / sec, "unit": UNIT, "ms_per_step": sec / steps * 1e3, "h2d_bytes_per_step": 8 * B,
+            "inference_sweep": {"value": len(pk) / sweep_sec, "unit": UNIT, "crystals": len(pk), "batch": B,
+                                "note": "evaluate.sweep: ids -> on-device collate (length-sorted batches) -> forward, "
+                                        "per-crystal evaluation, host wall clock incl. launch overhead"},
             "d2h_bytes_per_step": 4, "collate_ms": cms, "collate_gbytes_per_s": nbytes / (cms * 1e-3) / 1e9,
             "collate_launches": len(pk.tables) + 2, "store_bytes": pk.nbytes(), "crystals_in_store": len(pk),
             "note": "crystal ids from host memory -> PackedCrystals.collate (segmented copies on the device) -> fwd+bwd; "

@@ -922,7 +922,9 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     DOST_REQUIRE(pl.hi && (!split3 || pl.lo), "gemm_bf16: B planes missing");
     DOST_REQUIRE(al16(pl.hi) && al16(pl.lo) && pl.ld % 8 == 0, "gemm_bf16: B planes must be 16-byte aligned, ld %% 8 == 0");
     int rc;
-    const bool ragged_b = batch > 1 && h->b_rowoff != nullptr;   // one 2-D plane of pl.rows rows, per-problem row offsets
+    // one 2-D plane of pl.rows rows, per-problem row offsets.  Also with a single problem (a batch of one crystal): the
+    // map must end at the stored rows, so that the K / N padding reads zeros instead of whatever follows the allocation
+    const bool ragged_b = h->b_rowoff != nullptr;
     if (ragged_b) {
       DOST_REQUIRE(pl.rows > 0, "gemm_bf16: ragged B needs the total number of stored rows");
       if (!b_mc) {
@@ -953,10 +955,11 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   p.zmode = split > 1 ? 2 : (batch > 1 ? 1 : 0);
   p.c_bstride = h->c_bstride;
   p.res_bstride = h->res_bstride;
-  p.b_rowoff = batch > 1 ? h->b_rowoff : nullptr;
-  p.c_rowoff = batch > 1 ? h->c_rowoff : nullptr;
-  p.c_rowlim = batch > 1 ? h->c_rowlim : nullptr;
+  p.b_rowoff = h->b_rowoff;      // honoured for a single problem too (index 0): the row limit keeps the padded rows of a
+  p.c_rowoff = h->c_rowoff;      // one-crystal batch from being written past the output
+  p.c_rowlim = h->c_rowlim;
   DOST_REQUIRE(!p.c_rowoff || p.c_rowlim, "gemm_bf16: ragged output needs both c_rowoff and c_rowlim");
+  DOST_REQUIRE(split == 1 || !(p.b_rowoff || p.c_rowoff || p.c_rowlim), "gemm_bf16: ragged problems cannot be split along K");
   p.kchunk = 0;
   p.ws = nullptr;
   if (split > 1) {

@@ -48,3 +48,42 @@ def evaluate(model, batches: Iterable, mode: str = "edos", device=None):
     mean = per.double().mean(0).cpu()              # the only device->host read of the sweep (besides the returned arrays)
     preds_y = [ids, torch.cat(preds_all).cpu().numpy(), torch.cat(y_all).cpu().numpy(), torch.cat(emb_all).cpu().numpy()]
     return float(mean[1]), float(mean[0]), float(mean[2]), float(mean[3]), [preds_y]
+
+
+def sweep_plan(node_count, batch_size: int, world: int = 1):
+    """Host-side plan of an inference sweep over a packed store (BASELINE config 5: "sharded contiguous-by-length"):
+    crystals sorted by atom count (stable), cut into batches of ``batch_size`` neighbours in that order (a batch's
+    padding-free work is then uniform), batches dealt round-robin to the ranks.  Returns per rank a list of int64 id
+    tensors; every crystal appears exactly once."""
+    import numpy as np
+    order = np.argsort(np.asarray(node_count), kind="stable")
+    batches = [torch.from_numpy(order[i:i + batch_size].astype(np.int64)) for i in range(0, len(order), batch_size)]
+    return [batches[r::world] for r in range(world)]
+
+
+@torch.no_grad()
+def sweep(model, store, batch_size: int = 512, rank: int = 0, world: int = 1, clamp: bool = True):
+    """Forward-only DOS prediction of every crystal of ``store`` (a collate.PackedCrystals) assigned to this rank: batches
+    are assembled on the device from crystal ids, evaluated per crystal (``per_crystal_eval``: no padding coupling between
+    crystals, like the reference's batch_size-1 test loaders, utils.py:61-112) and the predictions are scattered into one
+    device buffer; nothing is read back per batch.  Returns (ids [n_local] int64 on the device, dos_system [n_local, T],
+    dos_global [n_local, T]), rows in the order of ``ids``; predictions clamped at 0 like utils.py:76 if ``clamp``."""
+    plan = sweep_plan(store.node_count, batch_size, world)[rank]
+    was_training, was_pc = model.training, model.per_crystal_eval
+    model.eval()
+    model.per_crystal_eval = True
+    ids_all, sys_all, glob_all = [], [], []
+    try:
+        for ids in plan:
+            g = store.collate(ids)
+            dos_global, _, dos_system = model(g)
+            ids_all.append(ids)
+            sys_all.append(dos_system.clamp_min(0) if clamp else dos_system)
+            glob_all.append(dos_global.clamp_min(0) if clamp else dos_global)
+    finally:
+        model.per_crystal_eval = was_pc
+        model.train(was_training)
+    if not ids_all:
+        dev = store.device
+        return torch.zeros(0, dtype=torch.int64, device=dev), torch.zeros(0, 0, device=dev), torch.zeros(0, 0, device=dev)
+    return torch.cat(ids_all).to(store.device), torch.cat(sys_all), torch.cat(glob_all)

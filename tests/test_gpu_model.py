@@ -120,7 +120,7 @@ def test_phonon_h256_golden_from_seed():
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("B,H,seed", [(16, 64, 1), (3, 128, 2), (1, 32, 3), (40, 256, 4)])
+@pytest.mark.parametrize("B,H,seed", [(16, 64, 1), (3, 128, 2), (1, 32, 3), (40, 256, 4), (1, 128, 5), (1, 256, 6)])
 def test_edos_against_oracle_fresh_batches(B, H, seed, prec):
     torch.manual_seed(seed)
     m = DOSTransformer(3, 2, 200, 41, 2, H, torch.device(DEV), 0.0, precision=prec)
@@ -348,3 +348,28 @@ def test_device_collate_bit_exact(kind):
         b = model(hb)
     for u, v in zip(a, b):
         assert torch.equal(u, v)
+
+
+def test_inference_sweep_matches_per_crystal_forward():
+    """evaluate.sweep over a packed store == the model run on each crystal alone (the reference's batch_size-1 test loop),
+    for every crystal exactly once, across a 2-rank split."""
+    from dostransformer_b200.collate import PackedCrystals, split_batch
+    from dostransformer_b200.evaluate import sweep
+    src = make_edos_batch(21, seed=41)
+    graphs = split_batch(src)
+    store = PackedCrystals.from_graphs(graphs, device=DEV)
+    torch.manual_seed(1)
+    model = DOSTransformer(2, 1, 200, 41, 2, 128, torch.device(DEV), 0.0).to(DEV)
+    got = {}
+    for rank in range(2):
+        ids, ds, dg = sweep(model, store, batch_size=4, rank=rank, world=2)
+        assert ds.shape == (ids.numel(), 201) and bool((ds >= 0).all())
+        for i, a, b in zip(ids.tolist(), ds, dg):
+            assert i not in got
+            got[i] = (a, b)
+    assert sorted(got) == list(range(21)) and model.training and not model.per_crystal_eval
+    model.eval()
+    with torch.no_grad():
+        for i in (0, 7, 20):
+            dg1, _, ds1 = model(store.collate([i]))
+            assert relerr(got[i][0], ds1[0].clamp_min(0)) < 1e-4 and relerr(got[i][1], dg1[0].clamp_min(0)) < 1e-4

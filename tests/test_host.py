@@ -199,3 +199,21 @@ def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
     # and nothing in the C struct is missing from the mirror: equal size + equal last-field offset covers trailing fields
+
+
+def test_sweep_plan_covers_every_crystal_once():
+    import numpy as np
+    from dostransformer_b200.evaluate import sweep_plan
+    rng = np.random.default_rng(0)
+    counts = rng.integers(2, 60, size=1000)
+    for world in (1, 3, 8):
+        plan = sweep_plan(counts, 64, world)
+        assert len(plan) == world
+        allids = np.concatenate([b.numpy() for r in plan for b in r])
+        assert sorted(allids.tolist()) == list(range(1000))
+        # contiguous by length: inside a batch the atom counts span a narrow range, batches are balanced across ranks
+        for r in plan:
+            for b in r:
+                c = counts[b.numpy()]
+                assert c.max() - c.min() <= 6
+        assert max(len(r) for r in plan) - min(len(r) for r in plan) <= 1
