@@ -119,8 +119,8 @@ class ClockSampler:
 def make_batches(rank: int, nb: int, B: int, workload: str = "edos"):
     from dostransformer_b200.synthetic import make_edos_batch, make_large_cell_batch
     if workload == "large":      # BASELINE configs[3]: 200-400 atoms per crystal, 24 neighbours (not the headline line)
-        return [make_large_cell_batch(B, seed=4000 + 1000 * rank + i) for i in range(nb)]
-    return [make_edos_batch(B, seed=2000 + 1000 * rank + i) for i in range(nb)]
+        return [make_large_cell_batch(B, seed=4000 + 1000 * rank + i, T=T) for i in range(nb)]
+    return [make_edos_batch(B, seed=2000 + 1000 * rank + i, T=T) for i in range(nb)]
 
 
 def flops_per_crystal_fwd(n_nodes: float, n_edges: float, nmax: float) -> float:
@@ -239,7 +239,7 @@ def kernel_rooflines(B: int, pk, precision: str):
         out["roofline_bf16_mode"] = six_gemms("bf16")     # the same kernel reading only the hi planes (1 MMA per product)
     # scatter_sum as a CSR segmented reduction: [E,256] -> [N,256]
     from dostransformer_b200.synthetic import make_edos_batch
-    g = make_edos_batch(B, seed=2000)
+    g = make_edos_batch(B, seed=2000, T=T)
     gr = ops.build_graph(g.edge_index.to(dev), g.batch.to(dev), g.system.to(dev))
     dst = torch.empty(gr.N, HIDDEN, device=dev)
     big = [torch.randn(gr.E, HIDDEN, device=dev) for _ in range(max(1, int(300e6 // (gr.E * HIDDEN * 4))))]
@@ -310,7 +310,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
     if args.nmax > 0:
         nmax = max(nmax, args.nmax)
     torch.manual_seed(0)
-    model = DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, dev, 0.0, precision=args.precision).to(dev).train()
+    model = DOSTransformer(GNN_LAYERS, T_LAYERS, 200, 41, 2, HIDDEN, dev, 0.0, n_energies=T, precision=args.precision).to(dev).train()
     model.max_num_nodes = nmax            # global padding length: the only cross-rank coupling besides the grads
     reducer = GradReducer(live_named_parameters(model)) if (world > 1 and not os.environ.get("DOST_BENCH_NO_REDUCER")) else None
     weight = 1.0 / world
@@ -563,7 +563,11 @@ def main():
     ap.add_argument("--data-rank", type=int, default=-1, help="(experiments) generate the batches of another rank")
     ap.add_argument("--precision", default=os.environ.get("DOST_PRECISION", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="GEMM path: fp32 FMA pipe | tcgen05 bf16x3 (fp32 parity, default) | tcgen05 bf16")
+    ap.add_argument("--energies", type=int, default=T, help="energy-grid length (201 = the reference's eDOS grid; 1001 = the "
+                    "long-grid variant of the large-cell stress configuration); not the headline line when changed")
     args = ap.parse_args()
+    if args.energies != T:
+        globals()["T"] = args.energies
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

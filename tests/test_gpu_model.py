@@ -377,3 +377,28 @@ def test_inference_sweep_matches_per_crystal_forward():
         for i in (0, 7, 20):
             dg1, _, ds1 = model(store.collate([i]))
             assert relerr(got[i][0], ds1[0].clamp_min(0)) < 1e-4 and relerr(got[i][1], dg1[0].clamp_min(0)) < 1e-4
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_long_energy_grid_against_oracle(prec):
+    """BASELINE config 4's long energy grid (T = 1001 instead of 201): 1001-wide self-attention rows (the softmax kernels'
+    upper range), ragged cross-attention with 1001 queries per crystal, B*T not a multiple of the 128-row tile."""
+    T = 1001
+    torch.manual_seed(11)
+    m = DOSTransformer(1, 1, 200, 41, 2, 128, torch.device(DEV), 0.0, n_energies=T, precision=prec)
+    sd = O.state_dict_of(m)
+    g = make_edos_batch(3, seed=61, mean_atoms=15.0, max_atoms=80, T=T)
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    g64 = g.clone()
+    for k in g64.keys():
+        v = getattr(g64, k)
+        if torch.is_tensor(v) and v.is_floating_point():
+            setattr(g64, k, v.double())
+    (rdg, rx, rds), rloss, rgrads = O.run_train_step(O.edos_forward, O.edos_loss, sd64, g64, g64.y_ft)
+    _, _, rgrads32 = O.run_train_step(O.edos_forward, O.edos_loss, sd, g, g.y_ft)
+    m.to(DEV)
+    dg, x, ds, loss, grads = _step(m, g.clone().to(DEV), "edos")
+    assert dg.shape == (3, T)
+    assert relerr(dg, rdg) < 1e-4 and relerr(ds, rds) < 1e-4 and relerr(x, rx) < 1e-4
+    assert abs(loss.item() - rloss.item()) < 1e-4 * abs(rloss.item())
+    _check_grads(grads, rgrads32, rgrads, floor=GRAD_FLOOR[prec])
