@@ -187,7 +187,8 @@ def dos_heads(model, x_nodes, graph: ops.CrystalGraph, graph_vec, prompt_table, 
         h = cross_stack(model.transformer_source, h, x_nodes, graph, B, T, seeds)
         return ops.linear([(h.view(B * T, H), None)], model.out_layer.weight, model.out_layer.bias).view(B, T)
 
-    if ops.tc_active(e2d) and ops.planes_gemm_ok(B * T, H, H) and not L.switch("DOST_NO_HEADSPLIT"):
+    if ops.tc_active(e2d) and ops.planes_gemm_ok(B * T, H, H) and not L.switch("DOST_NO_HEADSPLIT") \
+            and not L.switch("DOST_NO_LINPLANES"):       # the row-group bias lives in the planes GEMM's epilogue
         # split weights: the per-crystal terms (graph vector, prompt embedding) are multiplied once per crystal and enter
         # the [B*T, H] GEMM as a row-group bias instead of being broadcast over the T energy tokens
         wf, wp = model.fc.weight, model.fc_prompt.weight
