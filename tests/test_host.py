@@ -217,3 +217,28 @@ def test_sweep_plan_covers_every_crystal_once():
                 c = counts[b.numpy()]
                 assert c.max() - c.min() <= 6
         assert max(len(r) for r in plan) - min(len(r) for r in plan) <= 1
+
+
+def test_bench_reference_arm_contract_and_product_arm_needs_gpu():
+    """bench.py --impl reference prints one JSON line with the contract's keys (CPU oracle port, bounded sample); the
+    product arm refuses to run without a CUDA device instead of falling back to the CPU."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-sample", "4"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "crystals/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["vs_baseline"] is None and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=300, cwd=ROOT)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
