@@ -66,6 +66,9 @@ class AdamW:
         L.check(L.lib().dost_adamw_step(n, arr(ps), arr(gs), arr(ms), arr(vs), (C.c_longlong * n)(*ns), float(grp["lr"]),
                                         float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]),
                                         float(grp["weight_decay"]), self._step, L.stream()), "adamw_step")
+        # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on the tensors'
+        # version counters, e.g. the bf16 operand planes of the weights in ops.weight_planes) that they changed
+        torch.autograd.graph.increment_version(live)
 
     def state_dict(self):
         idx = {p: i for i, p in enumerate(self.params)}
