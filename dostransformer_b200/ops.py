@@ -313,7 +313,7 @@ def weight_planes(w: torch.Tensor) -> Planes:
     base = w._base if w._base is not None else w
     cache = base.__dict__.setdefault("_dost_weight_planes", {})
     key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), _PRECISION != L.PREC_BF16)
-    ver = base._version
+    ver = (base._version, base.data_ptr())     # the address too: `p.data = other` swaps storage without a version bump
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
