@@ -129,3 +129,19 @@ def edos_graph_batch(lattice, pos, node_ptr, atom_feats: torch.Tensor, radius: f
     nmax = int(counts.max().item()) + 1 if C else 0
     return CrystalBatch(x=x, edge_index=edge_index, edge_attr=e["edge_attr"], batch=batch, max_num_nodes=nmax,
                         **per_crystal)
+
+
+def phonon_graph_batch(lattice, pos, node_ptr, x: torch.Tensor, r_max: float = 4.0, **per_crystal):
+    """Structures -> the phonon model's input batch on the device (utils.build_data, utils.py:249-303, then the PyG
+    collate): ``x`` [N,118] are the mass-weighted one-hot rows of the atoms (the element table stays on the host),
+    edges = every periodic image within ``r_max`` including the self-interaction images, ``edge_vec`` = pos[dst] - pos[src]
+    + shift @ lattice.  ``per_crystal`` tensors (``system`` [C], ``phdos`` [C,51] ...) are passed through."""
+    from .synthetic import CrystalBatch
+    nl = phonon_edges(lattice, pos, node_ptr, r_max)
+    dev = pos.device
+    node_ptr = node_ptr.to(device=dev, dtype=torch.int64)
+    C = node_ptr.numel() - 1
+    counts = node_ptr[1:] - node_ptr[:-1]
+    batch = torch.repeat_interleave(torch.arange(C, device=dev, dtype=torch.int64), counts, output_size=pos.shape[0])
+    return CrystalBatch(x=x.to(dev), edge_index=nl["edge_index"], edge_vec=nl["edge_vec"], edge_shift=nl["edge_shift"],
+                        batch=batch, **per_crystal)

@@ -125,3 +125,37 @@ def test_edos_graph_batch_feeds_the_model():
     from dostransformer_b200.synthetic import CrystalBatch
     ref = O.edos_forward(sd, CrystalBatch(**{k: v for k, v in want.items() if k != "ptr"}))
     assert (dg.cpu() - ref[0]).abs().max() <= 1e-4 * ref[0].abs().max()
+
+
+def test_phonon_graph_batch_feeds_the_model():
+    """Structures -> phonon graph -> model on the device, against the oracle-built graph through the CPU oracle model."""
+    from dostransformer_b200.embedder_phDOS.DOSTransformer_phonon import DOSTransformer_phonon
+    from dostransformer_b200.synthetic import CrystalBatch
+    from oracle import dost_oracle as O
+    torch.set_default_dtype(torch.float64)
+    sizes = [2, 5, 3]
+    cells, lattice, pos, node_ptr = _batch(14, sizes, 3.0, 5.5)
+    gen = torch.Generator().manual_seed(4)
+    N, C = sum(sizes), len(sizes)
+    x = torch.zeros(N, 118)
+    x[torch.arange(N), torch.randint(0, 118, (N,), generator=gen)] = 1.0 + 200.0 * torch.rand(N, generator=gen)
+    system = torch.randint(0, 7, (C,), generator=gen)
+    got = NB.phonon_graph_batch(lattice, pos, node_ptr, x.to(DEV), r_max=4.0, system=system.to(DEV))
+    graphs, off = [], 0
+    for b, ((L, p), n) in enumerate(zip(cells, sizes)):
+        nl = NO.neighbor_list(L, p, 4.0, self_interaction=True)
+        graphs.append({"x": x[off:off + n], "edge_index": torch.tensor(np.stack([nl["src"], nl["dst"]])),
+                       "edge_vec": torch.tensor(nl["vec"]), "system": system[b]})
+        off += n
+    want = O.collate(graphs)
+    for k in ("x", "edge_index", "edge_vec", "batch", "system"):
+        assert torch.equal(got[k].cpu(), want[k]), k
+    torch.manual_seed(0)
+    model = DOSTransformer_phonon(2, 1, 118, 4, 64, torch.device(DEV), 0.0).to(DEV).eval()
+    with torch.no_grad():
+        dg, xx, ds = model(got)
+    assert dg.shape == (C, 51) and bool(torch.isfinite(dg).all()) and bool(torch.isfinite(ds).all())
+    sd = O.state_dict_of(model.cpu())
+    ref = O.phonon_forward(sd, CrystalBatch(**{k: v for k, v in want.items() if k != "ptr"}))
+    assert (dg.cpu() - ref[0]).abs().max() <= 1e-5 * ref[0].abs().max()
+    assert (ds.cpu() - ref[2]).abs().max() <= 1e-5 * ref[2].abs().max()
