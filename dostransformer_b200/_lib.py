@@ -22,6 +22,9 @@ PREC_FMA, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FMA, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 _lib: Optional[C.CDLL] = None
+ABI_VERSION = 9
+DEVERR_MESSAGES = {1: "an index (edge_index / batch / system) is outside its table",
+                   2: "a crystal has more atoms than the padding length given by the host (max_num_nodes)"}
 
 
 class Seg(C.Structure):
@@ -73,6 +76,9 @@ _SIGNATURES = {
     "dost_last_error": (C.c_char_p, []),
     "dost_launch_count": (C.c_longlong, []),
     "dost_reset_launch_count": (None, []),
+    "dost_device_errors_init": (C.c_int, []),
+    "dost_device_errors": (C.c_uint, [C.c_int]),
+    "dost_imax_scalar": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "dost_cast_i64_i32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dost_csr_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_longlong]),
     "dost_csr_build": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -182,7 +188,7 @@ def load(path: str = LIB_PATH) -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.dost_abi_version() != 8:
+    if lib.dost_abi_version() != ABI_VERSION:
         raise RuntimeError("libdost_b200.so ABI version mismatch")
     _lib = lib
     return lib
@@ -198,14 +204,32 @@ def lib() -> C.CDLL:
     if not _cuda_checked:
         if not torch.cuda.is_available():
             raise RuntimeError("dostransformer_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        torch.cuda.init()
+        check(L.dost_device_errors_init(), "device_errors_init")
         _cuda_checked = True
     return L
+
+
+def poll_device_errors() -> None:
+    """Raises if a kernel of an EARLIER, completed launch flagged invalid input (no device synchronisation: the flags live
+    in mapped host memory).  Called at the start of every ops.build_graph; call it after torch.cuda.synchronize() to
+    check the most recent step."""
+    if _lib is None:
+        return
+    mask = int(_lib.dost_device_errors(1))
+    if mask:
+        msgs = [m for bit, m in DEVERR_MESSAGES.items() if mask & bit]
+        raise RuntimeError("dostransformer_b200: a kernel skipped invalid input: " + "; ".join(msgs))
 
 
 def check(rc: int, what: str = "") -> None:
     if rc != 0:
         msg = load().dost_last_error().decode("utf-8", "replace")
         raise RuntimeError(f"libdost_b200 {what} failed (rc={rc}): {msg}")
+
+
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_get_device = getattr(torch._C, "_cuda_getDevice", None)
 
 
 def dt(t: torch.Tensor) -> int:
@@ -222,11 +246,13 @@ def p(t: Optional[torch.Tensor]):
         return None
     if not t.is_cuda:
         raise RuntimeError("dostransformer_b200: tensor is not on a CUDA device (no CPU fallback)")
+    if _get_device is not None and t.get_device() != _get_device():
+        # kernels launch on the CURRENT device's current stream: a tensor of another device would be dereferenced there
+        raise RuntimeError(f"dostransformer_b200: tensor on cuda:{t.get_device()} but the current device is "
+                           f"cuda:{_get_device()}; wrap the call in torch.cuda.device(tensor.device)")
     return C.c_void_p(t.data_ptr())
 
 
-_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
-_get_device = getattr(torch._C, "_cuda_getDevice", None)
 
 
 def stream():

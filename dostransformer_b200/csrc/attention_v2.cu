@@ -455,10 +455,10 @@ static int launch_fwd(const float* q, long long q_ss, const float* kv, const flo
                       unsigned int thresh, float inv_keep, unsigned long long seed, cudaStream_t st) {
   constexpr int H = 128 * NF;
   const size_t smem = sizeof(float) * (32 * H + 32 * (H + 4) + kWarps * 32 * 4);
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice cfg_once;
+  if (bool* cfg_flag = cfg_once.pending()) {
     cudaFuncSetAttribute(fwd_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
+    *cfg_flag = true;
   }
   dim3 grid(ceil_div(Tn, kQB), S);
   fwd_kernel<NF><<<grid, kWarps * 32, smem, st>>>(q, q_ss, kv, phantom, ptr, nmax, resid, r_ss, out, lse, S, B, Tn, scale, thresh,
@@ -474,11 +474,11 @@ static int launch_bwd(const float* dO, const float* q, long long q_ss, const flo
   constexpr int H = 128 * NF;
   const size_t smem_q = sizeof(float) * (2 * 32 * H + 32 * (H + 4) + kWarps * 32 * 4);
   const size_t smem_kv = sizeof(float) * (2 * 32 * H + 32 * (H + 4) + 2 * 32 * 32);
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice cfg_once;
+  if (bool* cfg_flag = cfg_once.pending()) {
     cudaFuncSetAttribute(bwd_q_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
     cudaFuncSetAttribute(bwd_kv_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_kv);
-    configured = true;
+    *cfg_flag = true;
   }
   dim3 grid(ceil_div(Tn, kQB), S);
   bwd_q_kernel<NF><<<grid, kWarps * 32, smem_q, st>>>(dO, q, q_ss, kv, phantom, ptr, nmax, out, resid, r_ss, lse, dq, Dbuf, part, S, B,

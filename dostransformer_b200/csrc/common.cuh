@@ -8,10 +8,41 @@
 
 namespace dost {
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (grid-size heuristics; persistent kernels query sm_count())
+
+// SM count of the current device (cached per device index).
+inline int sm_count() {
+  static int cached[64] = {};
+  int d = 0;
+  cudaGetDevice(&d);
+  d &= 63;
+  if (cached[d] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = kNumSMs;
+    cached[d] = n;
+  }
+  return cached[d];
+}
+
+// cudaFuncSetAttribute is per device: one flag per (kernel instantiation, device).  Usage:
+//   static PerDevice cfg; if (bool* f = cfg.pending()) { ...set attribute...; *f = true; }
+struct PerDevice {
+  bool done[64] = {};
+  bool* pending() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    return done[d] ? nullptr : &done[d];
+  }
+};
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// Device-visible error words (mapped host memory; nullptr until dost_device_errors_init): word i <-> bit (1 << i) of
+// dost_device_errors().  Kernels raise a flag with `if (errw) errw[kErrIndexRange] = 1u;`.
+constexpr int kDevErrWords = 8;
+constexpr int kErrIndexRange = 0, kErrNmaxTooSmall = 1;
+unsigned int* device_error_words();
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();

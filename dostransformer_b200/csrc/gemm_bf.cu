@@ -821,22 +821,24 @@ static int launch(const Maps& maps, const Params& p, cudaStream_t st) {
   constexpr int NSTAGE = NSTAGE_RAW < kMaxStages ? NSTAGE_RAW : kMaxStages;
   const int smem = NSTAGE * STAGE_BYTES + kEpiBytes + 1024;
   auto kern = gemm_bf_kernel<NSPLIT, BN, CTA2>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice cfg_once;
+  if (bool* cfg_flag = cfg_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("gemm_bf16: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return DOST_ERR_LAUNCH;
     }
-    configured = true;
+    *cfg_flag = true;
   }
   if (!CTA2) {
-    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    const int sms = sm_count();
+    const int grid = p.total_tiles < sms ? p.total_tiles : sms;
     kern<<<grid, kThreads, smem, st>>>(maps, p);
     return check_launch("gemm_bf16");
   }
   // CTA pairs: clusters of 2 along x, one pair per 256-row tile, persistent over the tiles
-  const int pairs = p.total_tiles < kNumSMs / 2 ? p.total_tiles : kNumSMs / 2;
+  const int half_sms = sm_count() / 2;
+  const int pairs = p.total_tiles < half_sms ? p.total_tiles : half_sms;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(kThreads);

@@ -638,16 +638,17 @@ static int launch_one(const GemmDev<float>& g, const Sched& sch, cudaStream_t st
   constexpr int NSTAGE = (kSmemBudget / STAGE_BYTES) < kMaxStages ? (kSmemBudget / STAGE_BYTES) : kMaxStages;
   const int smem = NSTAGE * STAGE_BYTES + 1024;
   auto kern = gemm_tc_kernel<NSPLIT, BN, A_MC, B_MC>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDevice cfg_once;
+  if (bool* cfg_flag = cfg_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
       set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       return DOST_ERR_LAUNCH;
     }
-    configured = true;
+    *cfg_flag = true;
   }
-  const int grid = sch.total_tiles < kNumSMs ? sch.total_tiles : kNumSMs;
+  const int sms = sm_count();
+  const int grid = sch.total_tiles < sms ? sch.total_tiles : sms;
   kern<<<grid, kThreads, smem, st>>>(g, sch);
   return check_launch("gemm_tc");
 }

@@ -10,10 +10,17 @@ __global__ void cast_i64_i32_kernel(const long long* __restrict__ src, int* __re
   for (; i < n; i += stride) dst[i] = static_cast<int>(src[i]);
 }
 
-__global__ void hist_kernel(const int* __restrict__ key, int* __restrict__ cnt, long long n) {
+// Keys outside [0, size) are skipped (they belong to no segment) and reported through the device error word: the
+// reference raises IndexError there; writing cnt[key] unchecked would corrupt the neighbouring allocations.
+__global__ void hist_kernel(const int* __restrict__ key, int* __restrict__ cnt, long long n, long long size,
+                            unsigned int* __restrict__ errw) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) atomicAdd(&cnt[key[i]], 1);  // integer counts: order independent
+  for (; i < n; i += stride) {
+    const int k = key[i];
+    if (static_cast<unsigned long long>(k) < static_cast<unsigned long long>(size)) atomicAdd(&cnt[k], 1);  // integer counts
+    else if (errw) errw[kErrIndexRange] = 1u;
+  }
 }
 
 // Single-block exclusive scan of cnt[size] -> rowptr[size+1], cursor[size]; also max(cnt).
@@ -55,11 +62,14 @@ __global__ void __launch_bounds__(1024) scan_kernel(const int* __restrict__ cnt,
   }
 }
 
-__global__ void fill_kernel(const int* __restrict__ key, int* __restrict__ cursor, int* __restrict__ tmp, long long n) {
+__global__ void fill_kernel(const int* __restrict__ key, int* __restrict__ cursor, int* __restrict__ tmp, long long n,
+                            long long size) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
-    int pos = atomicAdd(&cursor[key[i]], 1);
+    const int k = key[i];
+    if (static_cast<unsigned long long>(k) >= static_cast<unsigned long long>(size)) continue;
+    int pos = atomicAdd(&cursor[k], 1);
     tmp[pos] = static_cast<int>(i);
   }
 }
@@ -93,9 +103,19 @@ __global__ void rank_sort_kernel(const int* __restrict__ rowptr, const int* __re
   }
 }
 
+__global__ void imax_scalar_kernel(int* __restrict__ v, int floor_value) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && *v < floor_value) *v = floor_value;
+}
+
 }  // namespace dost
 
 using namespace dost;
+
+extern "C" int dost_imax_scalar(int32_t* value, int32_t floor_value, dost_stream_t stream) {
+  DOST_REQUIRE(value, "imax_scalar: null pointer");
+  imax_scalar_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(value, floor_value);
+  return check_launch("imax_scalar");
+}
 
 extern "C" int dost_cast_i64_i32(const int64_t* src, int32_t* dst, long long n, dost_stream_t stream) {
   if (n == 0) return DOST_OK;
@@ -123,14 +143,14 @@ extern "C" int dost_csr_build(const int32_t* key, long long n, long long size, i
   cudaMemsetAsync(cnt, 0, sizeof(int) * size, st);
   if (n > 0) {
     int blocks = min(ceil_div(n, 256), kNumSMs * 8);
-    hist_kernel<<<blocks, 256, 0, st>>>(key, cnt, n);
+    hist_kernel<<<blocks, 256, 0, st>>>(key, cnt, n, size, device_error_words());
     count_launch();
   }
   scan_kernel<<<1, 1024, 0, st>>>(cnt, rowptr, cursor, maxcount, size);
   count_launch();
   if (n > 0) {
     int blocks = min(ceil_div(n, 256), kNumSMs * 8);
-    fill_kernel<<<blocks, 256, 0, st>>>(key, cursor, tmp, n);
+    fill_kernel<<<blocks, 256, 0, st>>>(key, cursor, tmp, n, size);
     count_launch();
     int sblocks = min(ceil_div(size * 32, 256), kNumSMs * 16);
     rank_sort_kernel<<<sblocks, 256, 0, st>>>(rowptr, tmp, perm, size);

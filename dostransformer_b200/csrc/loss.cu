@@ -142,38 +142,54 @@ extern "C" int dost_loss_bwd(int dtype, int mode, const void* pred_g, const void
 namespace dost {
 
 template <typename T>
-__global__ void __launch_bounds__(128) eval_crystal_kernel(const T* __restrict__ pred, const T* __restrict__ y, int clamp_pred, int Tn,
+__global__ void __launch_bounds__(128) eval_crystal_kernel(const T* __restrict__ pred, const T* __restrict__ y, int clamp, int Tn,
                                                            T* __restrict__ per) {
+  // `clamp`: eDOS (utils.py:75-76 clamps BOTH the target and the prediction at 0); phonon (utils.py:127-131) clamps neither.
   __shared__ T red[4][4];
+  __shared__ T mean_s;
   const int b = blockIdx.x;
   const T* p = pred + (long long)b * Tn;
   const T* yy = y + (long long)b * Tn;
-  T sse = T(0), sae = T(0), sy = T(0), sy2 = T(0);
+  T sse = T(0), sae = T(0), sy = T(0);
   for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
     T yt = yy[t], pt = p[t];
-    if (yt < T(0)) yt = T(0);
-    if (clamp_pred && pt < T(0)) pt = T(0);
+    if (clamp && yt < T(0)) yt = T(0);
+    if (clamp && pt < T(0)) pt = T(0);
     const T d = yt - pt;
     sse = fma(d, d, sse);
     sae += (d < T(0) ? -d : d);
     sy += yt;
-    sy2 = fma(yt, yt, sy2);
   }
-  sse = warp_sum(sse); sae = warp_sum(sae); sy = warp_sum(sy); sy2 = warp_sum(sy2);
+  sse = warp_sum(sse); sae = warp_sum(sae); sy = warp_sum(sy);
   if ((threadIdx.x & 31) == 0) {
     const int w = threadIdx.x >> 5;
-    red[0][w] = sse; red[1][w] = sae; red[2][w] = sy; red[3][w] = sy2;
+    red[0][w] = sse; red[1][w] = sae; red[2][w] = sy;
   }
+  __syncthreads();
+  if (threadIdx.x == 0) mean_s = ((red[2][0] + red[2][1]) + (red[2][2] + red[2][3])) / T(Tn);
+  __syncthreads();
+  // total sum of squares around the mean in a second pass (sum y^2 - (sum y)^2 / T cancels in fp32)
+  const T mean = mean_s;
+  T sst = T(0);
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+    T yt = yy[t];
+    if (clamp && yt < T(0)) yt = T(0);
+    const T d = yt - mean;
+    sst = fma(d, d, sst);
+  }
+  sst = warp_sum(sst);
+  if ((threadIdx.x & 31) == 0) red[3][threadIdx.x >> 5] = sst;
   __syncthreads();
   if (threadIdx.x == 0) {
     T v[4];
     for (int k = 0; k < 4; ++k) v[k] = (red[k][0] + red[k][1]) + (red[k][2] + red[k][3]);
     const T mse = v[0] / T(Tn);
-    const T sst = v[3] - v[2] * v[2] / T(Tn);
     per[4 * b + 0] = mse;
     per[4 * b + 1] = sqrt(mse);
     per[4 * b + 2] = v[1] / T(Tn);
-    per[4 * b + 3] = T(1) - v[0] / sst;      // sklearn.metrics.r2_score of the flattened crystal (utils.py:20-23)
+    // sklearn.metrics.r2_score of the flattened crystal (utils.py:20-23); a constant target (sst == 0) scores 1 for a
+    // perfect prediction and 0 otherwise (sklearn's force_finite), not -inf / NaN
+    per[4 * b + 3] = (v[3] > T(0)) ? T(1) - v[0] / v[3] : (v[0] == T(0) ? T(1) : T(0));
   }
 }
 

@@ -78,12 +78,16 @@ template <int NPL>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ sc, const int* __restrict__ ptr,
                                                           const int* __restrict__ nmax_p, long long rows, int B, int Tn, int npad,
                                                           float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                          long long ldp, float* __restrict__ lse) {
+                                                          long long ldp, float* __restrict__ lse, unsigned int* __restrict__ errw) {
   const int lane = threadIdx.x & 31;
   const int nmax = *nmax_p;
   for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
     const int b = (int)((r / Tn) % B);
-    const int nb = __ldg(ptr + b + 1) - __ldg(ptr + b);
+    int nb = __ldg(ptr + b + 1) - __ldg(ptr + b);
+    if (nb + 1 > npad) {      // the host's padding length undercuts this crystal: reported, never read past the row
+      if (errw && lane == 0) errw[kErrNmaxTooSmall] = 1u;
+      nb = npad - 1;
+    }
     const int nph = max(nmax - nb, 0);
     const int ncol = nb + (nph > 0 ? 1 : 0);     // columns that take part: the real keys, then the phantom column
     float v[NPL];
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   const int nmax = *nmax_p;
   for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
     const int b = (int)((r / Tn) % B);
-    const int nb = __ldg(ptr + b + 1) - __ldg(ptr + b);
+    const int nb = min(__ldg(ptr + b + 1) - __ldg(ptr + b), npad - 1);
     const int nph = max(nmax - nb, 0);
     const int ncol = nb + (nph > 0 ? 1 : 0);
     const float ls = __ldg(lse + r);
@@ -205,7 +209,8 @@ extern "C" int dost_xattn_softmax_fwd(const float* scores, const int32_t* ptr, c
   cudaStream_t st = (cudaStream_t)stream;
   const int npl = npl_for(ldp);
   const int blocks = (int)min64((rows + 7) / 8, 32LL * kNumSMs);
-  DOST_XTC_DISPATCH(softmax_fwd_kernel, scores, ptr, nmax, rows, B, T, npad, (float)scale, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp, lse)
+  DOST_XTC_DISPATCH(softmax_fwd_kernel, scores, ptr, nmax, rows, B, T, npad, (float)scale, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp, lse,
+                    device_error_words())
   return check_launch("xattn_softmax_fwd");
 }
 

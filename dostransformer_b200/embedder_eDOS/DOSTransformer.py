@@ -43,7 +43,10 @@ class DOSTransformer(nn.Module):
         self.max_num_nodes = None      # data-parallel: global padding length (phantom-key count) set by the sharder
 
     def forward(self, g):
-        with ops.precision(self.precision):
+        # kernels launch on the current device's current stream: make the model's device current for the call (the
+        # autograd engine does the same for the backward nodes)
+        with torch.cuda.device(self.fc.weight.device) if self.fc.weight.is_cuda else ops.nullcontext(), \
+                ops.precision(self.precision):
             return self._forward(g)
 
     def _forward(self, g):

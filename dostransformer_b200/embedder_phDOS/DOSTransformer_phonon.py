@@ -52,7 +52,10 @@ class DOSTransformer_phonon(nn.Module):
         self.max_num_nodes = None
 
     def forward(self, g):
-        with ops.precision(self.precision):
+        # kernels launch on the current device's current stream: make the model's device current for the call (the
+        # autograd engine does the same for the backward nodes)
+        with torch.cuda.device(self.fc.weight.device) if self.fc.weight.is_cuda else ops.nullcontext(), \
+                ops.precision(self.precision):
             return self._forward(g)
 
     def _forward(self, g):

@@ -39,7 +39,7 @@ def evaluate(model, batches: Iterable, mode: str = "edos", device=None):
             emb_all.append(ops.segment_reduce_raw(x.contiguous(), graph_ptr.rowptr, None, B))
             per_all.append(per)
             preds_all.append(pred.clamp_min(0) if clamp else pred)
-            y_all.append(target.clamp_min(0))
+            y_all.append(target.clamp_min(0) if clamp else target)
             ids += list(getattr(g, "mp_id", []))
     finally:
         model.per_crystal_eval = was_pc

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+from contextlib import nullcontext
 import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
@@ -158,6 +159,8 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
                 need_backward: bool = True, nmax_hint: Optional[int] = None, phantoms: bool = True) -> CrystalGraph:
     """edge_index int64 [2,E] (row = centre atom, col = neighbour), batch int64 [N] sorted, system int64 [B]."""
     assert edge_index.is_cuda, "dostransformer_b200 has no CPU path: move the batch to a CUDA device"
+    L.lib()
+    L.poll_device_errors()        # invalid input skipped by the kernels of an earlier step (no synchronisation)
     N, E, B = batch.numel(), edge_index.shape[1], system.numel()
     ei = to_i32(edge_index)
     row, col = ei[0], ei[1]
@@ -169,9 +172,20 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
         by_sys, _ = csr_build(s32, 7)
     crystals, nmax = csr_build(b32, B, want_max=True)
     crystals.perm = None
-    if nmax_override is not None:     # data-parallel: global padding length fixed by the sharder
-        nmax = torch.full((1,), int(nmax_override), dtype=torch.int32, device=batch.device)
-    host = int(nmax_override) if nmax_override is not None else (int(nmax_hint) if nmax_hint is not None else None)
+    # Padding length (to_dense_batch's Nmax).  `nmax_override` is the data-parallel global value set by the sharder; it
+    # may exceed this batch's own maximum but must never undercut it: a crystal with more atoms than the padding length
+    # would get a negative phantom-key count and, on the tensor-core attention path, more score columns than were
+    # allocated.  The batch's own maximum is known on the host when the collate recorded it (`nmax_hint`); otherwise the
+    # device value max(override, measured) is used and the host-sized tensor-core path is only taken with a hint.
+    if nmax_override is not None and nmax_hint is not None and int(nmax_override) < int(nmax_hint):
+        raise ValueError(f"max_num_nodes={int(nmax_override)} (model.max_num_nodes / sharder) is smaller than this batch's "
+                         f"largest crystal ({int(nmax_hint)} nodes): stale data-parallel padding length")
+    host = None
+    if nmax_override is not None:
+        L.check(L.lib().dost_imax_scalar(L.p(nmax), int(nmax_override), L.stream()), "imax_scalar")   # nmax = max(nmax, override)
+        host = int(nmax_override) if nmax_hint is not None else None
+    elif nmax_hint is not None:
+        host = int(nmax_hint)
     if not phantoms:      # per-crystal evaluation (the reference's batch_size-1 loaders): no padding, hence no phantom keys
         nmax = torch.zeros(1, dtype=torch.int32, device=batch.device)
     return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host)
@@ -307,15 +321,42 @@ def split_planes_colsum(x2d: torch.Tensor) -> Tuple[Planes, torch.Tensor]:
     return pl, cs
 
 
+_PLANES_GENERATION = 0
+
+
+def invalidate_weight_planes(model=None) -> None:
+    """Drops the cached bf16 operand planes of the weights (all of them, or those of ``model`` / an iterable of
+    parameters).  The cache is keyed on the parameter's autograd version counter and storage address, so optimizers that
+    update through ``p.add_()`` / ``p.copy_()`` / this package's fused AdamW are seen automatically; writes that BYPASS
+    the version counter are not - ``p.data.copy_()``, ``p.data.mul_()``, ``dist.broadcast(p.data)``, EMA swaps through
+    ``.data``, raw-pointer or graph-captured updates.  Call this after any such write (``dp.broadcast_parameters`` and
+    ``graphed.GraphedStep`` do).  ``DOST_CHECK_PLANES=1`` re-splits on every cache hit and raises on a stale entry."""
+    global _PLANES_GENERATION
+    if model is None:
+        _PLANES_GENERATION += 1
+        return
+    params = model.parameters() if hasattr(model, "parameters") else model
+    for p in params:
+        base = p._base if p._base is not None else p
+        base.__dict__.pop("_dost_weight_planes", None)
+
+
 def weight_planes(w: torch.Tensor) -> Planes:
     """Planes of a parameter (or of a strided view of one), cached ON the parameter object until it is modified in
     place (optimizer step).  Keying on the object - not on its address - keeps the cache exact across models."""
     base = w._base if w._base is not None else w
     cache = base.__dict__.setdefault("_dost_weight_planes", {})
     key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), _PRECISION != L.PREC_BF16)
-    ver = (base._version, base.data_ptr())     # the address too: `p.data = other` swaps storage without a version bump
+    # the address too: `p.data = other` swaps storage without a version bump
+    ver = (base._version, base.data_ptr(), _PLANES_GENERATION)
     hit = cache.get(key)
     if hit is not None and hit[0] == ver:
+        if L.switch("DOST_CHECK_PLANES"):
+            fresh = split_planes(w.detach())
+            same = torch.equal(fresh.hi, hit[1].hi) and (fresh.lo is None or torch.equal(fresh.lo, hit[1].lo))
+            if not same:
+                raise RuntimeError("stale weight planes: a parameter was written without bumping its version counter "
+                                   "(p.data.*, raw pointers); call ops.invalidate_weight_planes(model) after such writes")
         return hit[1]
     pl = split_planes(w.detach())
     cache[key] = (ver, pl)

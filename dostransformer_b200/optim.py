@@ -17,15 +17,31 @@ from . import _lib as L
 
 
 class AdamW:
-    def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+    def __init__(self, params: Iterable, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 1e-2):
-        self.params: List[torch.nn.Parameter] = [p for p in params]
-        if not self.params:
-            raise ValueError("optimizer got an empty parameter list")
         self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
-        self.param_groups = [dict(params=self.params, **self.defaults)]
+        params = list(params)
+        if not params:
+            raise ValueError("optimizer got an empty parameter list")
+        # torch.optim accepts either parameters or param-group dicts ({"params": [...], "lr": ...})
+        groups = params if isinstance(params[0], dict) else [dict(params=params)]
+        self.param_groups = []
+        seen = set()
+        for g in groups:
+            ps = [g["params"]] if isinstance(g["params"], torch.Tensor) else list(g["params"])
+            for p in ps:
+                if id(p) in seen:
+                    raise ValueError("some parameters appear in more than one parameter group")
+                seen.add(id(p))
+            extra = set(g) - {"params"} - set(self.defaults)
+            if extra:
+                raise ValueError(f"unknown param-group options {sorted(extra)}")
+            self.param_groups.append({**self.defaults, **{k: v for k, v in g.items() if k != "params"}, "params": ps})
         self.state = {}
-        self._step = 0
+
+    @property
+    def params(self) -> List[torch.nn.Parameter]:
+        return [p for g in self.param_groups for p in g["params"]]
 
     def zero_grad(self, set_to_none: bool = True) -> None:
         for p in self.params:
@@ -45,44 +61,61 @@ class AdamW:
 
     @torch.no_grad()
     def step(self) -> None:
-        grp = self.param_groups[0]
-        live = [p for p in self.params if p.grad is not None]
-        if not live:
-            return
-        self._step += 1
-        ps, gs, ms, vs, ns = [], [], [], [], []
-        keep = []      # contiguous gradient copies must outlive the launch
-        for p in live:
-            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
-                raise RuntimeError("dostransformer_b200.optim.AdamW handles contiguous fp32 CUDA parameters only")
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            keep.append(g)
-            st = self._state_of(p)
-            st["step"] = self._step
-            ps.append(p.data_ptr()); gs.append(g.data_ptr()); ms.append(st["exp_avg"].data_ptr())
-            vs.append(st["exp_avg_sq"].data_ptr()); ns.append(p.numel())
-        n = len(live)
-        arr = lambda xs: (C.c_void_p * n)(*xs)
-        L.check(L.lib().dost_adamw_step(n, arr(ps), arr(gs), arr(ms), arr(vs), (C.c_longlong * n)(*ns), float(grp["lr"]),
-                                        float(grp["betas"][0]), float(grp["betas"][1]), float(grp["eps"]),
-                                        float(grp["weight_decay"]), self._step, L.stream()), "adamw_step")
-        # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on the tensors'
-        # version counters, e.g. the bf16 operand planes of the weights in ops.weight_planes) that they changed
-        torch.autograd.graph.increment_version(live)
+        """One AdamW update of every parameter that has a gradient.  The step count (bias correction) is kept PER
+        PARAMETER like torch.optim.AdamW: a parameter whose gradient was None for some steps is corrected with its own
+        count.  Parameters of one group that share a count go into the same launches (32 tensors per launch)."""
+        touched = []
+        for grp in self.param_groups:
+            by_step = {}
+            for p in grp["params"]:
+                if p.grad is None:
+                    continue
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("dostransformer_b200.optim.AdamW handles contiguous fp32 CUDA parameters only")
+                st = self._state_of(p)
+                st["step"] += 1
+                by_step.setdefault(st["step"], []).append(p)
+            for step, live in by_step.items():
+                ps, gs, ms, vs, ns = [], [], [], [], []
+                keep = []      # contiguous gradient copies must outlive the launch
+                for p in live:
+                    g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                    keep.append(g)
+                    st = self.state[p]
+                    ps.append(p.data_ptr()); gs.append(g.data_ptr()); ms.append(st["exp_avg"].data_ptr())
+                    vs.append(st["exp_avg_sq"].data_ptr()); ns.append(p.numel())
+                n = len(live)
+                arr = lambda xs: (C.c_void_p * n)(*xs)
+                with torch.cuda.device(live[0].device):
+                    L.check(L.lib().dost_adamw_step(n, arr(ps), arr(gs), arr(ms), arr(vs), (C.c_longlong * n)(*ns),
+                                                    float(grp["lr"]), float(grp["betas"][0]), float(grp["betas"][1]),
+                                                    float(grp["eps"]), float(grp["weight_decay"]), step, L.stream()),
+                            "adamw_step")
+                touched += live
+        if touched:
+            # the kernel wrote the parameters through raw pointers: tell autograd (and every cache keyed on the tensors'
+            # version counters, e.g. the bf16 operand planes of the weights in ops.weight_planes) that they changed
+            torch.autograd.graph.increment_version(touched)
 
     def state_dict(self):
-        idx = {p: i for i, p in enumerate(self.params)}
+        plist = self.params
+        idx = {p: i for i, p in enumerate(plist)}
+        groups, k = [], 0
+        for g in self.param_groups:
+            n = len(g["params"])
+            groups.append({**{kk: v for kk, v in g.items() if kk != "params"}, "params": list(range(k, k + n))})
+            k += n
         return {"state": {idx[p]: {"step": torch.tensor(float(st["step"])), "exp_avg": st["exp_avg"],
                                    "exp_avg_sq": st["exp_avg_sq"]} for p, st in self.state.items()},
-                "param_groups": [{**{k: v for k, v in self.param_groups[0].items() if k != "params"},
-                                  "params": list(range(len(self.params)))}]}
+                "param_groups": groups}
 
     def load_state_dict(self, sd) -> None:
+        plist = self.params
         for i, st in sd["state"].items():
-            p = self.params[int(i)]
+            p = plist[int(i)]
             self.state[p] = dict(step=int(float(st["step"])), exp_avg=st["exp_avg"].to(p.device).clone(),
                                  exp_avg_sq=st["exp_avg_sq"].to(p.device).clone())
-            self._step = max(self._step, self.state[p]["step"])
-        for k, v in sd["param_groups"][0].items():
-            if k != "params":
-                self.param_groups[0][k] = v
+        for g, saved in zip(self.param_groups, sd["param_groups"]):
+            for k, v in saved.items():
+                if k != "params":
+                    g[k] = v

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 8
+#define DOST_ABI_VERSION 9
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -43,6 +43,16 @@ const char* dost_last_error(void);
 long long dost_launch_count(void);
 void dost_reset_launch_count(void);
 
+/* Device-side input checks.  Kernels that meet invalid input they can skip (an index outside its table, a padding
+ * length shorter than a crystal) skip it and raise a bit in one word of mapped host memory, so the host can poll it
+ * WITHOUT a device synchronisation (a bit is visible once the kernel that raised it has completed).  The reference
+ * raises IndexError at the same places (x[row] DOSTransformer.py:139-140, scatter index :187, promt_token[g.system]
+ * :79).  dost_device_errors_init() allocates the word (call once per process before any CUDA-graph capture; returns
+ * 0 or DOST_ERR_LAUNCH); dost_device_errors(clear) returns the bit mask and optionally clears it. */
+enum { DOST_DEVERR_INDEX_RANGE = 1, DOST_DEVERR_NMAX_TOO_SMALL = 2 };
+int dost_device_errors_init(void);
+unsigned int dost_device_errors(int clear);
+
 /* ---------------------------------------------------------------------------------------------
  * Integer graph structure (bit-exact work).  Replaces the index handling implied by
  * torch_scatter.scatter_sum/mean (DOSTransformer.py:187, DOSTransformer_phonon.py:209),
@@ -56,6 +66,10 @@ int dost_cast_i64_i32(const int64_t* src, int32_t* dst, long long n, dost_stream
 size_t dost_csr_workspace_bytes(long long n, long long size);
 int dost_csr_build(const int32_t* key, long long n, long long size, int32_t* rowptr, int32_t* perm,
                    int32_t* maxcount, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+
+/* *value = max(*value, floor_value) on the device (one int): the data-parallel padding length Nmax = max(this rank's
+ * measured maximum, the sharder's global value) without a device->host read (to_dense_batch's max()). */
+int dost_imax_scalar(int32_t* value, int32_t floor_value, dost_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * GEMM family (fp32/fp64 FMA pipe, or tcgen05 tensor cores for fp32 data).  C[m,n] = epilogue( sum_k A(m,k) * B(n,k) ).
@@ -295,8 +309,10 @@ int dost_loss_bwd(int dtype, int mode, const void* pred_g, const void* pred_s, c
                   dost_stream_t stream);
 
 /* Evaluation metrics of utils.test / utils.test_phonon (utils.py:61-143), on the device: per crystal (the reference
- * evaluates with batch_size 1) targets clamped at 0 (and predictions if clamp_pred: eDOS, utils.py:74-76),
- * per_crystal [B,4] = (mse, rmse, mae, r2 = 1 - SSE / sum (y - mean y)^2); mean [4] (optional) = their means over crystals. */
+ * evaluates with batch_size 1); clamp_pred != 0 (eDOS, utils.py:75-76) clamps BOTH targets and predictions at 0,
+ * clamp_pred == 0 (phonon, utils.py:127-131) clamps neither.  per_crystal [B,4] = (mse, rmse, mae,
+ * r2 = 1 - SSE / sum (y - mean y)^2, two-pass; a constant target scores 1 if SSE == 0 else 0 like sklearn's r2_score);
+ * mean [4] (optional) = their means over crystals. */
 int dost_eval_metrics(int dtype, const void* pred, const void* y, int clamp_pred, int B, int T, void* per_crystal, void* mean,
                       dost_stream_t stream);
 
