@@ -168,3 +168,55 @@ def make_phonon_batch(B: int = 1, seed: int = 1000, *, K: int = 24, min_atoms: i
     ph = ph / ph.amax(dim=1, keepdim=True)
     return CrystalBatch(x=x.to(dtype), edge_index=torch.stack([src, dst]), edge_vec=v.to(dtype), batch=batch,
                         system=system, phdos=ph.to(dtype))
+
+
+def pad_edos_batch(g: CrystalBatch, *, node_bucket: int = 256, dummies: int = 8, nmax_bucket: int = 32,
+                   T: int = EDOS_T) -> CrystalBatch:
+    """Pads an eDOS batch to bucketed shapes so that CUDA-graph replay (graphed.GraphedStep) sees few distinct signatures.
+
+    ``dummies`` zero-feature dummy crystals are appended (each = some atoms + the zero node of mat2graph.py:155-158, every
+    atom with the data set's fixed out-degree pointing at itself, zero targets) so that the node count becomes a multiple
+    of ``node_bucket``; with a fixed out-degree the edge count follows.  ``n_valid`` = the number of real crystals: the
+    loss is taken over the first ``n_valid`` rows only, so the dummies receive exactly zero gradient and contribute
+    exactly zero to every weight gradient.  No dummy is larger than the largest real crystal, hence the padding length
+    Nmax (= every real crystal's phantom-key count) is unchanged; the host-side hint ``max_num_nodes`` is
+    rounded up to ``nmax_bucket`` (it only sizes buffers; the phantom count comes from the device-side maximum).
+    CPU tensors in, CPU tensors out (a collate-time operation)."""
+    B = int(g.system.numel())
+    N = int(g.batch.numel())
+    n_nodes = torch.bincount(g.batch, minlength=B)
+    nmax = int(n_nodes.max())
+    E = int(g.edge_index.shape[1])
+    n_atoms = N - B
+    K = E // max(n_atoms, 1)
+    if n_atoms <= 0 or K * n_atoms != E:
+        raise ValueError("pad_edos_batch needs the eDOS layout: one zero node per crystal and a fixed out-degree per atom")
+    D = int(dummies)
+    while True:
+        N_to = -(-(N + 2 * D) // node_bucket) * node_bucket
+        P = N_to - N
+        sizes = [P // D + (1 if j < P % D else 0) for j in range(D)]
+        if max(sizes) <= nmax or nmax < 2:
+            break
+        D *= 2
+    if nmax < 2:
+        raise ValueError("pad_edos_batch: the largest real crystal must have at least one atom")
+    xs, rows, batches = [g.x], [], [g.batch]
+    off = N
+    for j, s in enumerate(sizes):
+        atoms = torch.arange(off, off + s - 1, dtype=torch.int64)
+        rows.append(atoms.repeat_interleave(K))
+        batches.append(torch.full((s,), B + j, dtype=torch.int64))
+        off += s
+    row_pad = torch.cat(rows) if rows else torch.zeros(0, dtype=torch.int64)
+    xs.append(torch.zeros(P, g.x.shape[1], dtype=g.x.dtype))
+    hint = -(-(nmax + 1) // nmax_bucket) * nmax_bucket - 1
+    out = CrystalBatch(
+        x=torch.cat(xs), edge_index=torch.cat([g.edge_index, torch.stack([row_pad, row_pad])], dim=1),
+        edge_attr=torch.cat([g.edge_attr, torch.zeros(row_pad.numel(), g.edge_attr.shape[1], dtype=g.edge_attr.dtype)]),
+        glob=torch.cat([g.glob, torch.zeros(2 * D, dtype=g.glob.dtype)]), batch=torch.cat(batches),
+        system=torch.cat([g.system, torch.zeros(D, dtype=g.system.dtype)]),
+        y_ft=torch.cat([g.y_ft, torch.zeros(D * T, dtype=g.y_ft.dtype)]),
+        mp_id=list(getattr(g, "mp_id", [f"c{i}" for i in range(B)])) + [f"pad-{j}" for j in range(D)],
+        max_num_nodes=hint, n_valid=B)
+    return out

@@ -1,0 +1,52 @@
+"""CUDA-path data-parallel parity (SURVEY.md 8e "parity definition"): two ranks over NCCL, the LPT sharder, the CUDA model
+per rank and the bucketed overlapped GradReducer must reproduce the single-GPU gradients of the concatenated global batch,
+and be bit-identical across repeated runs.  Skipped unless two GPUs are visible (`gpurun --gpus 2`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from dostransformer_b200 import dp, ops
+from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+from dostransformer_b200.synthetic import make_edos_batch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# rel-L2 per tensor between the 2-rank and the 1-rank gradients: both are the same math with a different summation
+# grouping (per-rank partial sums, then one addition), so only rounding differs
+TOL = {"fp32": 2e-5, "bf16x3": 1e-4}
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_two_gpu_reduced_gradients_equal_single_gpu(tmp_path, precision):
+    hidden, B = 128, 10
+    port = 29600 + os.getpid() % 1000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "_dp_gpu_worker.py"), str(tmp_path), precision, str(hidden), str(B)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    res = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    assert res["nbuckets"] > 1
+    a, b = res["runs"]
+    for k in a:                                                   # deterministic kernels + fixed bucket order
+        assert torch.equal(a[k], b[k]), f"{k}: reduced gradient differs between two runs"
+    # single GPU, whole batch
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    model = DOSTransformer(2, 2, 200, 41, 2, hidden, dev, 0.0, precision=precision).to(dev).train()
+    g = make_edos_batch(B, seed=11, mean_atoms=9.0).to(dev)
+    assert res["nmax"] == g.max_num_nodes
+    dg, x, ds = model(g)
+    loss = ops.dos_loss(dg, ds, g.y_ft, mode="edos", beta=1.0)
+    loss.backward()
+    assert abs(res["loss"] - loss.item()) <= 1e-5 * abs(loss.item())
+    live = {k for k, _ in dp.live_named_parameters(model)}
+    assert live == set(a)
+    for k, p in dp.live_named_parameters(model):
+        ref = p.grad.detach().cpu().double()
+        for name, got in (("reducer", a[k]), ("graphed", res["graphed"][k])):
+            err = ((got.double() - ref).norm() / ref.norm().clamp_min(1e-30)).item()
+            assert err < TOL[precision], (name, k, err)

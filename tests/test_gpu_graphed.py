@@ -1,0 +1,114 @@
+"""Whole-step CUDA-graph replay (dostransformer_b200.graphed) against the eager step: same kernels, same order, so
+losses and gradients must be BITWISE equal; bucket-padded batches must leave the real crystals' loss and gradients
+unchanged up to fp32 summation order."""
+import pytest
+import torch
+
+from dostransformer_b200 import ops
+from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+from dostransformer_b200.graphed import GraphedStep, batch_signature
+from dostransformer_b200.optim import AdamW
+from dostransformer_b200.synthetic import make_edos_batch, pad_edos_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(h=128, seed=0, prec="bf16x3"):
+    torch.manual_seed(seed)
+    return DOSTransformer(2, 2, 200, 41, 2, h, torch.device(DEV), 0.0, precision=prec).to(DEV).train()
+
+
+def _eager(m, g, weight=1.0):
+    m.zero_grad(set_to_none=True)
+    dg, _, ds = m(g)
+    loss = ops.dos_loss(dg, ds, g.y_ft, mode="edos", beta=1.0)
+    if weight != 1.0:
+        loss = loss * weight
+    loss.backward()
+    return loss.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+
+@pytest.mark.parametrize("prec", ["bf16x3", "fp32"])
+def test_graph_replay_is_bitwise_the_eager_step(prec):
+    m = _model(prec=prec)
+    step = GraphedStep(m, "edos")
+    sizes = torch.tensor([5, 9, 3, 12, 7, 8])
+    a = [make_edos_batch(6, seed=10 + i, sizes=sizes).to(DEV) for i in range(3)]       # one signature, three batches
+    b = [make_edos_batch(4, seed=20 + i, sizes=sizes[:4] + 2).to(DEV) for i in range(2)]  # a second signature
+    assert batch_signature(a[0]) == batch_signature(a[1]) != batch_signature(b[0])
+    for g in (a[0], b[0], a[1], b[1], a[2], a[0]):
+        want_loss, want = _eager(m, g)
+        got_loss = step(g)
+        assert torch.equal(got_loss.detach(), want_loss)
+        got = {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+        assert set(got) == set(want)
+        for k in want:
+            assert torch.equal(got[k], want[k]), k
+    assert step.captures == 2 and step.replays == 6 and step.launches > 0
+
+
+def test_graph_replay_sees_optimizer_updates():
+    """The weights' bf16 operand planes are re-split inside the graph: a replay after an optimizer step (fused AdamW
+    writes through raw pointers) must equal the eager step on the updated weights."""
+    m = _model()
+    step = GraphedStep(m, "edos")
+    opt = AdamW(m.parameters(), lr=1e-2, weight_decay=1e-2)
+    g = make_edos_batch(5, seed=31, mean_atoms=8.0).to(DEV)
+    l0 = step(g).detach().clone()
+    for _ in range(3):
+        opt.step()
+        step(g)
+    l1 = step(g).detach().clone()
+    want_loss, want = _eager(m, g)
+    assert torch.equal(l1, want_loss) and not torch.equal(l0, l1)
+    step(g)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            assert torch.equal(p.grad, want[k]), k
+    # a write that bypasses the version counter is seen too (the graph never trusts the cache)
+    with torch.no_grad():
+        m.fc.weight.data.mul_(1.5)
+    l2 = step(g).detach().clone()
+    ops.invalidate_weight_planes(m)
+    want2, _ = _eager(m, g)
+    assert torch.equal(l2, want2)
+
+
+def test_bucket_padding_leaves_the_real_crystals_unchanged():
+    m = _model(h=128)
+    g = make_edos_batch(7, seed=41, mean_atoms=9.0)
+    p = pad_edos_batch(g, node_bucket=64, dummies=3)
+    assert p.n_valid == 7 and p.system.numel() == 10 and p.x.shape[0] % 64 == 0
+    n = torch.bincount(p.batch)
+    assert int(n[7:].max()) <= int(n[:7].max())
+    want_loss, want = _eager(m, g.clone().to(DEV))
+    step = GraphedStep(m, "edos")
+    for _ in range(2):
+        got_loss = step(p.clone().to(DEV))
+    assert abs(got_loss.item() - want_loss.item()) <= 1e-6 * abs(want_loss.item())
+    for k, pr in m.named_parameters():
+        if k in want:
+            err = ((pr.grad.double() - want[k].double()).norm() / want[k].double().norm().clamp_min(1e-30)).item()
+            assert err < 2e-5, (k, err)
+    # model outputs of the real crystals are the unpadded ones
+    m.eval()
+    with torch.no_grad():
+        dg_p, x_p, ds_p = m(p.clone().to(DEV))
+        dg, x, ds = m(g.clone().to(DEV))
+    assert (dg_p[:7] - dg).abs().max().item() <= 1e-5 * dg.abs().max().item()
+    assert (x_p[:x.shape[0]] - x).abs().max().item() <= 1e-5 * x.abs().max().item()
+
+
+def test_graphed_inference_matches_eager():
+    m = _model().eval()
+    m.per_crystal_eval = True
+    step = GraphedStep(m, "edos", train=False)
+    gs = [make_edos_batch(5, seed=50 + i, sizes=torch.tensor([4, 6, 2, 9, 5])).to(DEV) for i in range(3)]
+    for g in gs:
+        with torch.no_grad():
+            want = m(g)
+        got = step(g)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    assert step.captures == 1
