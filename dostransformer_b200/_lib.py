@@ -89,6 +89,8 @@ _SIGNATURES = {
     "dost_gemm_bf16": (C.c_int, [C.POINTER(GemmBf16), C.c_void_p, C.c_size_t, C.c_void_p]),
     "dost_split_planes": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong,
                                     C.c_void_p]),
+    "dost_split_planes_multi": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "dost_split_planes_colsum_workspace_bytes": (C.c_size_t, [C.c_longlong, C.c_int, C.c_longlong]),
     "dost_split_planes_colsum": (C.c_int, [C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong,
                                            C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

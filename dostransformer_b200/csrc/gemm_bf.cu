@@ -35,6 +35,8 @@ constexpr int kSmemBudget = 225 * 1024;         // stages + staging (+ 1 KB alig
 struct Maps {
   CUtensorMap a_hi[3], a_lo[3], b_hi, b_lo;
   CUtensorMap b_hi2, b_lo2;      // K-major B with a 128-row box (CTA pair: each CTA stages half of the 256 output columns)
+  // TMA-store epilogue (Params::tma_epi): fp32 out {32 columns, 32 rows} boxes, SWIZZLE_128B; bf16 planes {32, 32}, SWIZZLE_64B
+  CUtensorMap c_out, c_hi, c_lo;
 };
 
 struct Params {
@@ -57,6 +59,8 @@ struct Params {
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_op;
   float* ws;
   float* colpart;               // [ceil(M / 32)][N] per-32-row column sums of the stored value (bias gradients)
+  int tma_epi;                  // epilogue variant: values finished in the accumulator's own layout (thread = row), staged in
+                                // the TMA-swizzled layout and written with cp.async.bulk.tensor stores (no second register pass)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -222,6 +226,24 @@ __device__ __forceinline__ uint2 ldg64_nc_if(const void* p, bool ok) {
   uint2 v = make_uint2(0u, 0u);
   asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q ld.global.nc.v2.b32 {%0, %1}, [%2];\n\t}"
                : "+r"(v.x), "+r"(v.y)
+               : "l"(p), "r"((uint32_t)ok)
+               : "memory");
+  return v;
+}
+
+// ---- TMA store (shared -> global) of one box, bulk async-group completion
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint4 ldg128u_nc_if(const void* p, bool ok) {
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t@q ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+               : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w)
                : "l"(p), "r"((uint32_t)ok)
                : "memory");
   return v;
@@ -442,11 +464,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     // round trips per chunk with only two epilogue warps per scheduler to hide them).  The empty asm statements keep the
     // compiler from rematerialising the loads.
     enum : uint32_t { F_BIAS = 1, F_ROWBIAS = 2, F_PRE = 4, F_ACT = 8, F_DACT = 16, F_RES = 32, F_OUT = 64, F_ACC = 128,
-                      F_HI = 256, F_LO = 512, F_COLPART = 1024, F_SPLITK = 2048, F_ROWLIM = 4096 };
+                      F_HI = 256, F_LO = 512, F_COLPART = 1024, F_SPLITK = 2048, F_ROWLIM = 4096, F_TMA = 8192 };
     uint32_t feat = (p.bias ? F_BIAS : 0u) | (p.rowbias ? F_ROWBIAS : 0u) | (p.out_pre ? F_PRE : 0u) |
                     (p.act != DOST_ACT_NONE ? F_ACT : 0u) | (p.dact_hi ? F_DACT : 0u) | (p.residual ? F_RES : 0u) |
                     (p.out ? F_OUT : 0u) | (p.accumulate ? F_ACC : 0u) | (p.out_hi ? F_HI : 0u) | (p.out_lo ? F_LO : 0u) |
-                    (p.colpart ? F_COLPART : 0u) | (p.zmode == 2 ? F_SPLITK : 0u) | (p.c_rowlim ? F_ROWLIM : 0u);
+                    (p.colpart ? F_COLPART : 0u) | (p.zmode == 2 ? F_SPLITK : 0u) | (p.c_rowlim ? F_ROWLIM : 0u) |
+                    (p.tma_epi ? F_TMA : 0u);
     int Mv = p.M, Nv = p.N;
     long long ldc_v = p.ldc, ldop_v = p.ld_op, ldres_v = p.ld_res;
     const float* bias_v = p.bias;
@@ -468,6 +491,142 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
       const int nbase = t.n0 + half * CH + cj * 4;
       uint32_t r[32];
       tmem_ld32(taddr0, r);
+      if (feat & F_TMA) {
+        // ---------------------------------------------------------------------------------- TMA-store epilogue
+        // Everything happens in the accumulator's own layout (tcgen05.ld 32x32b: thread = row, 32 consecutive columns
+        // in registers): bias / row bias / activation / act' mask / residual are applied there, the finished values
+        // are written once into this warp's staging tile in the TMA swizzle, and one elected lane issues the
+        // cp.async.bulk.tensor store.  TMA clips rows >= M and columns >= N.  No transposed second register pass, no
+        // per-thread global address arithmetic or predicated stores.
+        const int mrow = t.m0 + quad * 32 + lane;
+        const bool row_ok = mrow < Mv;
+        const bool warp_rows_ok = t.m0 + quad * 32 < Mv;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CH; c0 += 32) {
+          const int n0 = t.n0 + half * CH + c0;            // first column of the chunk (warp-uniform)
+          const bool live = warp_rows_ok && n0 < Nv;
+          uint4 sg[4];
+          if ((feat & F_DACT) && live) {                   // activation-derivative mask: 32 bf16 of this thread's row
+            const __nv_bfloat16* dp = p.dact_hi + (long long)mrow * p.ld_dact + n0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sg[j] = ldg128u_nc_if(dp + 8 * j, row_ok && n0 + 8 * j < Nv);
+          }
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (c0 + 32 < CH) {
+            tmem_ld32(taddr0 + c0 + 32, r);                // next chunk streams in while this one is processed
+          } else {                                         // last read of this accumulator: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (CTA2) mbar_arrive_cluster(acce_remote0 + 8 * buf);
+              else mbar_arrive(acce0 + 8 * buf);
+            }
+          }
+          if (!live) continue;
+          if (feat & F_BIAS) {                             // the same 32 values for every lane: broadcast loads
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = ldg128_nc_if(bias_v + n0 + 4 * j, n0 + 4 * j < Nv);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (feat & F_ROWBIAS) {
+            const float* rb = p.rowbias + (long long)(mrow / p.rowbias_div) * p.ld_rowbias + n0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = ldg128_nc_if(rb + 4 * j, row_ok && n0 + 4 * j < Nv);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (feat & F_ACT) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = (v[j] > 0.f) ? v[j] : pslope * v[j];
+          }
+          if (feat & F_DACT) {
+            const float ds = p.dact_slope;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t w[4] = {sg[j].x, sg[j].y, sg[j].z, sg[j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float m0 = __uint_as_float(w[q] << 16), m1 = __uint_as_float(w[q] & 0xFFFF0000u);
+                v[8 * j + 2 * q] = (m0 > 0.f) ? v[8 * j + 2 * q] : ds * v[8 * j + 2 * q];
+                v[8 * j + 2 * q + 1] = (m1 > 0.f) ? v[8 * j + 2 * q + 1] : ds * v[8 * j + 2 * q + 1];
+              }
+            }
+          }
+          if (feat & F_RES) {
+            const float* rp = res_v + (long long)mrow * ldres_v + n0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q = ldg128_nc_if(rp + 4 * j, row_ok && n0 + 4 * j < Nv);
+              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+            }
+          }
+          // the previous chunk's store must have finished READING the staging tile before it is overwritten
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          if (feat & F_OUT) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else {                                         // bf16 hi (and lo) planes: 64-byte rows, SWIZZLE_64B
+            uint32_t hi[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            const uint32_t sw = (lane >> 1) & 3;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              sts128(stg + lane * 64 + ((c ^ sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            if (feat & F_LO) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                uint32_t lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const int j = 4 * c + q;
+                  lo[q] = pack_bf16(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xFFFF0000u));
+                }
+                sts128(stg + 2048 + lane * 64 + ((c ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+              }
+            }
+          }
+          fence_async_smem();                              // generic-proxy smem writes -> visible to the async proxy (TMA)
+          __syncwarp();
+          if (lane == 0) {
+            const int mw = t.m0 + quad * 32;
+            if (feat & F_OUT) {
+              tma_store_2d(&maps.c_out, stg, n0, mw);
+            } else {
+              tma_store_2d(&maps.c_hi, stg, n0, mw);
+              if (feat & F_LO) tma_store_2d(&maps.c_lo, stg + 2048, n0, mw);
+            }
+            bulk_commit();
+          }
+          if (feat & F_COLPART) {
+            // column sums over this warp's 32 rows by recursive halving across the lanes (31 shuffles, fixed order):
+            // afterwards lane L holds the sum of column L.  Rows past M do not count.
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+#pragma unroll
+            for (int sft = 16; sft >= 1; sft >>= 1) {
+              const bool upper = (lane & sft) != 0;
+#pragma unroll
+              for (int i = 0; i < sft; ++i) {
+                const float send = upper ? v[i] : v[i + sft];
+                const float keep = upper ? v[i + sft] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+              }
+            }
+            if (n0 + lane < Nv) p.colpart[(long long)((t.m0 + quad * 32) >> 5) * p.N + n0 + lane] = v[0];
+          }
+        }
+        continue;      // next tile
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < CH; c0 += 32) {
         const int n = nbase + c0;
@@ -613,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         }
       }
     }
+    if ((feat & F_TMA) && lane == 0) bulk_wait0();         // the staging tile must outlive the last store's read
   }
 
   tc_fence_before();
@@ -652,6 +812,55 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, long long rows, int cols,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int ldp, int vec_ok) {
   const int chunks = ldp / 8;                      // 8 elements (16 bytes of bf16) per thread step
+  const long long total = rows * chunks;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    const long long r = i / chunks;
+    const int c = static_cast<int>(i - r * chunks) * 8;
+    float v[8];
+    const float* src = x + r * ld + c;
+    if (vec_ok && c + 8 <= cols) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? __ldg(src + j) : 0.f;
+    }
+    uint4 h, l;
+    uint32_t* hp = &h.x;
+    uint32_t* lp = &l.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      hp[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+      lp[j] = pack_bf16(v[2 * j] - __uint_as_float(hp[j] << 16), v[2 * j + 1] - __uint_as_float(hp[j] & 0xFFFF0000u));
+    }
+    *reinterpret_cast<uint4*>(hi + r * ldp + c) = h;
+    if (lo) *reinterpret_cast<uint4*>(lo + r * ldp + c) = l;
+  }
+}
+
+// The same conversion for up to kMultiSplit tensors in ONE launch (the weights of the model, once per step): the tensor
+// descriptors travel in the kernel-parameter space, blockIdx.y selects the tensor.
+constexpr int kMultiSplit = 24;
+struct MultiSplit {
+  const float* x[kMultiSplit];
+  __nv_bfloat16* hi[kMultiSplit];
+  __nv_bfloat16* lo[kMultiSplit];
+  long long ld[kMultiSplit];
+  long long rows[kMultiSplit];
+  int cols[kMultiSplit];
+  int ldp[kMultiSplit];
+};
+__global__ void __launch_bounds__(256) split_planes_multi_kernel(const MultiSplit ms) {
+  const int t = blockIdx.y;
+  const float* __restrict__ x = ms.x[t];
+  __nv_bfloat16* __restrict__ hi = ms.hi[t];
+  __nv_bfloat16* __restrict__ lo = ms.lo[t];
+  const long long ld = ms.ld[t], rows = ms.rows[t];
+  const int cols = ms.cols[t], ldp = ms.ldp[t];
+  const int vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld % 4 == 0) ? 1 : 0;
+  const int chunks = ldp / 8;
   const long long total = rows * chunks;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -733,21 +942,25 @@ __global__ void __launch_bounds__(256) split_planes_colsum_kernel(const float* _
 
 // 32 columns x 32 row lanes per block: lane ry sums chunks ry, ry + 32, ... (four independent loads in flight), lanes are
 // combined in order (deterministic).  Only ceil(W / 32) blocks exist, so each keeps as many loads in flight as it can.
-__global__ void __launch_bounds__(1024) colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out) {
+__global__ void __launch_bounds__(1024) colsum_stage2_kernel(const float* __restrict__ ws, int nchunks, int W, float* __restrict__ out,
+                                                             int per_y) {
+  // blockIdx.y reduces chunks [y * per_y, min(nchunks, (y + 1) * per_y)) into out[y][W] (a single y: the final sums)
   __shared__ float sm[32][33];
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
+  const int cbeg = blockIdx.y * per_y;
+  const int cnt = min(per_y, nchunks - cbeg);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   if (c < W) {
-    const float* src = ws + c;
+    const float* src = ws + (long long)cbeg * W + c;
     int b = ry;
-    for (; b + 96 < nchunks; b += 128) {
+    for (; b + 96 < cnt; b += 128) {
       s0 += src[(long long)b * W];
       s1 += src[(long long)(b + 32) * W];
       s2 += src[(long long)(b + 64) * W];
       s3 += src[(long long)(b + 96) * W];
     }
-    for (; b < nchunks; b += 32) s0 += src[(long long)b * W];
+    for (; b < cnt; b += 32) s0 += src[(long long)b * W];
   }
   sm[ry][cx] = (s0 + s1) + (s2 + s3);
   __syncthreads();
@@ -755,8 +968,24 @@ __global__ void __launch_bounds__(1024) colsum_stage2_kernel(const float* __rest
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 32; ++k) t += sm[k][cx];
-    out[c] = t;
+    out[(long long)blockIdx.y * W + c] = t;
   }
+}
+
+// Column sums of `nchunks` partial rows in a fixed order.  Many partial rows (one per 32 output rows of a large GEMM) are
+// first reduced by kMidRows row groups in parallel (only ceil(W / 32) blocks would otherwise walk the whole table).
+constexpr int kMidRows = 32;
+static int colsum_reduce(const float* ws, int nchunks, int W, float* mid, float* out, cudaStream_t st) {
+  if (nchunks > 8 * kMidRows && mid) {
+    const int per = (nchunks + kMidRows - 1) / kMidRows;
+    const int ny = (nchunks + per - 1) / per;
+    colsum_stage2_kernel<<<dim3(ceil_div(W, 32), ny), 1024, 0, st>>>(ws, nchunks, W, mid, per);
+    count_launch();
+    colsum_stage2_kernel<<<dim3(ceil_div(W, 32), 1), 1024, 0, st>>>(mid, ny, W, out, ny);
+  } else {
+    colsum_stage2_kernel<<<dim3(ceil_div(W, 32), 1), 1024, 0, st>>>(ws, nchunks, W, out, nchunks);
+  }
+  return check_launch("column sums");
 }
 
 static inline int split_colsum_chunks(long long rows, int ldp) {
@@ -811,6 +1040,35 @@ static int make_map(CUtensorMap* m, const void* base, long long inner, long long
     return DOST_ERR_ARG;
   }
   return DOST_OK;
+}
+
+// 2-D output map for the TMA-store epilogue: [outer rows][inner elements contiguous], row pitch ld elements, box {32, 32}.
+static int make_out_map(CUtensorMap* m, const void* base, bool is_f32, long long inner, long long outer, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("gemm_bf16: cuTensorMapEncodeTiled is not available");
+    return DOST_ERR_UNSUPPORTED;
+  }
+  const int esz = is_f32 ? 4 : 2;
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+  cuuint32_t box[2] = {32u, 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) base=%p inner=%lld outer=%lld ld=%lld", (int)r, base, inner,
+              outer, ld);
+    return DOST_ERR_ARG;
+  }
+  return DOST_OK;
+}
+
+// The TMA-store epilogue (DOST_GEMM_TMA_EPI=0 disables it): one kind of output (fp32 or planes), plain single problem.
+static bool tma_epi_enabled() {      // read per call: the parity test flips it between two launches of one process
+  const char* e = getenv("DOST_GEMM_TMA_EPI");
+  return !(e && e[0] == '0');
 }
 
 template <int NSPLIT, int BN, bool CTA2>
@@ -996,7 +1254,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   const int nrb = (h->M + 31) / 32;
   if (h->colsum) {
     DOST_REQUIRE(split == 1 && batch == 1, "gemm_bf16: colsum needs a plain (single, un-split) problem");
-    const size_t need = sizeof(float) * (size_t)nrb * h->N;
+    const size_t need = sizeof(float) * ((size_t)nrb + kMidRows) * h->N;
     if (!workspace || workspace_bytes < need) {
       set_error("gemm_bf16: colsum workspace too small (%zu < %zu)", workspace_bytes, need);
       return DOST_ERR_WORKSPACE;
@@ -1013,6 +1271,26 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   DOST_REQUIRE(!h->out_hi || (((uintptr_t)h->out_hi & 7) == 0 && ((uintptr_t)h->out_lo & 7) == 0 && h->ld_op % 4 == 0),
                "gemm_bf16: output plane alignment");
 
+  // ---- TMA-store epilogue: exactly one kind of output, no pre-activation copy / accumulation / split-K / ragged rows
+  p.tma_epi = 0;
+  maps.c_out = maps.b_hi;
+  maps.c_hi = maps.b_hi;
+  maps.c_lo = maps.b_hi;
+  if (tma_epi_enabled() && split == 1 && batch == 1 && !h->out_pre && !h->accumulate && !p.c_rowoff && !p.c_rowlim &&
+      ((h->out != nullptr) != (h->out_hi != nullptr)) && h->M >= 32 && h->N >= 32 &&
+      (!h->dact_hi || (al16(h->dact_hi) && h->ld_dact % 8 == 0))) {
+    int rc2 = DOST_OK;
+    if (h->out) {
+      rc2 = make_out_map(&maps.c_out, h->out, true, h->N, h->M, h->ldc);
+    } else if (al16(h->out_hi) && al16(h->out_lo) && h->ld_op % 8 == 0) {
+      rc2 = make_out_map(&maps.c_hi, h->out_hi, false, h->N, h->M, h->ld_op);
+      if (rc2 == DOST_OK && h->out_lo) rc2 = make_out_map(&maps.c_lo, h->out_lo, false, h->N, h->M, h->ld_op);
+    } else {
+      rc2 = DOST_ERR_ARG;
+    }
+    if (rc2 == DOST_OK) p.tma_epi = 1;       // (a shape the encoder rejects simply keeps the register epilogue)
+  }
+
   int rc;
   if (pairs) {
     rc = split3 ? launch<3, 256, true>(maps, p, st) : launch<1, 256, true>(maps, p, st);
@@ -1025,8 +1303,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   }
   if (rc != DOST_OK) return rc;
   if (h->colsum) {
-    colsum_stage2_kernel<<<ceil_div(h->N, 32), 1024, 0, st>>>(p.colpart, nrb, h->N, h->colsum);
-    rc = check_launch("gemm_bf16 column sums");
+    rc = colsum_reduce(p.colpart, nrb, h->N, p.colpart + (size_t)nrb * h->N, h->colsum, st);
     if (rc != DOST_OK) return rc;
   }
   if (split > 1) {
@@ -1044,7 +1321,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
 
 extern "C" size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g) {
   if (!g) return 0;
-  if (g->colsum) return sizeof(float) * (size_t)((g->M + 31) / 32) * g->N;
+  if (g->colsum) return sizeof(float) * ((size_t)((g->M + 31) / 32) + dost::bf::kMidRows) * g->N;
   if (g->split_k <= 1) return 0;
   return sizeof(float) * (size_t)g->split_k * g->M * g->N;
 }
@@ -1077,8 +1354,42 @@ extern "C" int dost_split_planes_colsum(const float* x, long long ld, long long 
                                                              rpc, (float*)workspace);
   int rc = dost::check_launch("split_planes_colsum");
   if (rc != DOST_OK) return rc;
-  dost::bf::colsum_stage2_kernel<<<dost::ceil_div(cols, 32), 1024, 0, st>>>((const float*)workspace, nch, cols, colsum);
-  return dost::check_launch("split_planes_colsum stage2");
+  return dost::bf::colsum_reduce((const float*)workspace, nch, cols, nullptr, colsum, st);
+}
+
+extern "C" int dost_split_planes_multi(int ntensors, const float* const* x, const long long* ld, const long long* rows, const int* cols,
+                                       void* const* hi, void* const* lo, const long long* ldp, dost_stream_t stream) {
+  DOST_REQUIRE(ntensors >= 0 && x && ld && rows && cols && hi && lo && ldp, "split_planes_multi: null argument");
+  using dost::bf::kMultiSplit;
+  for (int t0 = 0; t0 < ntensors; t0 += kMultiSplit) {
+    dost::bf::MultiSplit ms;
+    const int nt = (ntensors - t0) < kMultiSplit ? (ntensors - t0) : kMultiSplit;
+    long long maxwork = 0;
+    for (int i = 0; i < kMultiSplit; ++i) {
+      const int j = t0 + (i < nt ? i : 0);
+      DOST_REQUIRE(i >= nt || (x[j] && hi[j] && rows[j] > 0 && cols[j] > 0 && ldp[j] >= cols[j] && ldp[j] % 8 == 0),
+                   "split_planes_multi: tensor %d: need rows > 0, ldp %% 8 == 0, ldp >= cols", j);
+      DOST_REQUIRE(i >= nt || (((uintptr_t)hi[j] & 15) == 0 && ((uintptr_t)lo[j] & 15) == 0),
+                   "split_planes_multi: tensor %d: planes must be 16-byte aligned", j);
+      ms.x[i] = x[j];
+      ms.hi[i] = (__nv_bfloat16*)hi[j];
+      ms.lo[i] = (__nv_bfloat16*)lo[j];
+      ms.ld[i] = ld[j];
+      ms.rows[i] = i < nt ? rows[j] : 0;
+      ms.cols[i] = cols[j];
+      ms.ldp[i] = (int)ldp[j];
+      const long long work = ms.rows[i] * (ldp[j] / 8);
+      if (work > maxwork) maxwork = work;
+    }
+    if (maxwork == 0) continue;
+    long long bx = (maxwork + 255) / 256;
+    if (bx > 64) bx = 64;
+    dim3 grid((unsigned)bx, nt);
+    dost::bf::split_planes_multi_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(ms);
+    int rc = dost::check_launch("split_planes_multi");
+    if (rc != DOST_OK) return rc;
+  }
+  return DOST_OK;
 }
 
 extern "C" int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,

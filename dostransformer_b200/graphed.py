@@ -25,7 +25,8 @@ Dropout > 0 draws a fresh host seed per step and therefore stays eager.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional, Tuple
+import gc
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -59,7 +60,7 @@ def allreduce_gradients(params, group=None, average: bool = False) -> None:
 
 
 class _Entry:
-    __slots__ = ("graph", "static", "out", "launches", "tensor_keys", "grads")
+    __slots__ = ("graph", "static", "out", "launches", "tensor_keys", "grads", "leaves")
 
 
 class GraphedStep:
@@ -85,15 +86,34 @@ class GraphedStep:
         self.replays = 0
         self.launches = 0          # kernels of this library executed by replays (captured count x replays)
         self._params = [p for p in model.parameters()]
+        self._stream = None
+        from .nn_core import gemm_weights
+        wid = {id(w) for w in gemm_weights(model)}
+        self._weight_names = [n for n, p in model.named_parameters() if id(p) in wid]
 
     # ------------------------------------------------------------------------------------------------------------
-    def _eager(self, g):
+    def _eager(self, g, refresh: bool = False, leaves=None):
         model = self.model
+        if leaves is not None:
+            # forward through fresh leaf aliases of the parameters (same storage): see _capture
+            return self._step_body(lambda b: torch.func.functional_call(model, leaves, (b,)), g, refresh, leaves)
+        return self._step_body(model, g, refresh, None)
+
+    def _step_body(self, forward, g, refresh, leaves):
+        model = self.model
+        if refresh and self._weight_names and getattr(model, "precision", "fp32") != "fp32":
+            named = leaves if leaves is not None else dict(model.named_parameters())
+            with ops.precision(model.precision):       # one launch per 24 weights instead of one per weight
+                ops.refresh_weight_planes([named[n] for n in self._weight_names])
         if not self.train:
             with torch.no_grad():
-                return model(g)
-        model.zero_grad(set_to_none=True)
-        dg, _, ds = model(g)
+                return forward(g)
+        if leaves is None:
+            model.zero_grad(set_to_none=True)
+        else:
+            for t in leaves.values():
+                t.grad = None
+        dg, _, ds = forward(g)
         nv = getattr(g, "n_valid", None)
         y = getattr(g, self.target_key)
         if nv is not None and nv != dg.shape[0]:        # bucket-padded batch: the dummy crystals never enter the loss
@@ -103,7 +123,7 @@ class GraphedStep:
         if self.loss_weight != 1.0:
             loss = loss * self.loss_weight
         loss.backward()
-        return loss
+        return loss.detach()       # (a loss with its grad_fn would keep the whole autograd graph of a capture alive)
 
     def _capturable(self) -> bool:
         return not (self.train and getattr(self.model, "attn_drop", 0.0) > 0.0)
@@ -114,25 +134,38 @@ class GraphedStep:
         e.tensor_keys = [k for k in g.keys() if torch.is_tensor(getattr(g, k))]
         e.static = CrystalBatch(**{k: (getattr(g, k).clone() if torch.is_tensor(getattr(g, k)) else getattr(g, k))
                                    for k in g.keys()})
-        # warm-up on a side stream (lazy one-time initialisation: kernel attributes, index caches, allocator pools)
-        s = torch.cuda.Stream(device=dev)
+        # Warm-up (lazy one-time initialisation: kernel attributes, index caches, allocator pools) on the SAME side stream
+        # the capture will use.  Autograd runs each parameter's AccumulateGrad node on the stream that was current when
+        # the node was created; a node that survives from an earlier eager iteration on the default stream would pull the
+        # legacy stream into the capture and invalidate it ("operation would make the legacy stream depend on a capturing
+        # blocking stream").  The captured step therefore differentiates with respect to FRESH leaf aliases of the
+        # parameters (p.detach(): same storage and version counter, so optimizer updates are seen; brand-new autograd
+        # identity, so its accumulator nodes are born on the capture stream) and hands their .grad to the parameters.
+        gc.collect()
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        s = self._stream
         s.wait_stream(torch.cuda.current_stream(dev))
+        e.leaves = None
         with torch.cuda.stream(s):
-            self._eager(e.static)
+            if self.train:
+                e.leaves = {n: p.detach().requires_grad_(p.requires_grad) for n, p in self.model.named_parameters()}
+            self._eager(e.static, leaves=e.leaves)
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
         L.poll_device_errors()
         ops.invalidate_weight_planes()      # the weights' operand planes must be produced inside the graph
-        if self.train:
-            self.model.zero_grad(set_to_none=True)
         e.graph = torch.cuda.CUDAGraph()
         l0 = L.launch_count()
-        with torch.cuda.graph(e.graph, pool=self._pool):
-            e.out = self._eager(e.static)
+        # thread_local: other threads of the process (NCCL's watchdog polling its events, the autograd engine's worker
+        # that launches the backward kernels into this capture) stay unrestricted; only this thread may not issue
+        # capture-unsafe calls
+        with torch.cuda.graph(e.graph, pool=self._pool, stream=s, capture_error_mode="thread_local"):
+            e.out = self._eager(e.static, refresh=True, leaves=e.leaves)
         e.launches = L.launch_count() - l0
         # the gradient buffers this graph writes (graph-pool memory, fixed addresses): re-attached on every replay, since
         # another signature's capture / replay leaves p.grad pointing at ITS buffers
-        e.grads = [p.grad for p in self._params] if self.train else None
+        e.grads = [e.leaves[n].grad for n, _ in self.model.named_parameters()] if self.train else None
         if self._pool is None:
             self._pool = e.graph.pool()
         ops.invalidate_weight_planes()      # eager calls must not keep pointing into the graph's pool

@@ -182,31 +182,51 @@ def dos_heads(model, x_nodes, graph: ops.CrystalGraph, graph_vec, prompt_table, 
     per_crystal = RowMap(div=T, div_rowptr=graph.token_rowptr(T))
     per_system = RowMap(idx=graph.system, div=T, div_rowptr=graph.token_rowptr(T), csr=graph.by_system)
 
-    def branch(dos_in):
-        h = self_stack(model.transformer_self, dos_in.view(B, T, H), seeds)
-        h = cross_stack(model.transformer_source, h, x_nodes, graph, B, T, seeds)
-        return ops.linear([(h.view(B * T, H), None)], model.out_layer.weight, model.out_layer.bias).view(B, T)
+    def branches(both, S):
+        """transformer_self -> transformer_source -> out_layer on S sequences (sequence s belongs to crystal s % B)."""
+        h = self_stack(model.transformer_self, both.view(S, T, H), seeds)
+        h = cross_stack(model.transformer_source, h, x_nodes, graph, S, T, seeds)
+        return ops.linear([(h.view(S * T, H), None)], model.out_layer.weight, model.out_layer.bias).view(S, T)
 
+    # The global and the system branch share transformer_self / transformer_source / out_layer
+    # (DOSTransformer.py:71-77 vs :85-91): they run as ONE batch of 2B sequences - half the launches, twice the rows per
+    # GEMM, and the shared weights receive one gradient instead of two that autograd would have to add.
+    batched = seeds.p == 0.0 and not L.switch("DOST_NO_BRANCH_BATCH")
+    buf = g_buf = s_buf = None
+    if batched:
+        buf, g_buf, s_buf = ops.stack2_buffer(B * T, B * T, H, e2d)
     if ops.tc_active(e2d) and ops.planes_gemm_ok(B * T, H, H) and not L.switch("DOST_NO_HEADSPLIT") \
             and not L.switch("DOST_NO_LINPLANES"):       # the row-group bias lives in the planes GEMM's epilogue
         # split weights: the per-crystal terms (graph vector, prompt embedding) are multiplied once per crystal and enter
         # the [B*T, H] GEMM as a row-group bias instead of being broadcast over the T energy tokens
         wf, wp = model.fc.weight, model.fc_prompt.weight
         rb_g = ops.linear([(graph_vec, None)], wf[:, H:], None)
-        g_in = ops.linear([(e2d, None)], wf[:, :H], model.fc.bias, act=L.ACT_LEAKY, act_slope=0.01, rowbias=rb_g, rowbias_div=T)
-        dos_global = branch(g_in)
+        g_in = ops.linear([(e2d, None)], wf[:, :H], model.fc.bias, act=L.ACT_LEAKY, act_slope=0.01, rowbias=rb_g, rowbias_div=T,
+                          out_buf=g_buf)
         rb_s = ops.linear([(graph_vec, None), (prompt_table, RowMap(idx=graph.system, csr=graph.by_system))], wp[:, H:], None,
                           M=B)
         s_in = ops.linear([(e2d, None)], wp[:, :H], model.fc_prompt.bias, act=L.ACT_LEAKY, act_slope=0.01, rowbias=rb_s,
-                          rowbias_div=T)
+                          rowbias_div=T, out_buf=s_buf)
     else:
         g_in = ops.linear([(e2d, None), (graph_vec, per_crystal)], model.fc.weight, model.fc.bias, M=B * T,
-                          act=L.ACT_LEAKY, act_slope=0.01)
-        dos_global = branch(g_in)
+                          act=L.ACT_LEAKY, act_slope=0.01, out_buf=g_buf)
         s_in = ops.linear([(e2d, None), (graph_vec, per_crystal), (prompt_table, per_system)], model.fc_prompt.weight,
-                          model.fc_prompt.bias, M=B * T, act=L.ACT_LEAKY, act_slope=0.01)
-    dos_system = branch(s_in)
+                          model.fc_prompt.bias, M=B * T, act=L.ACT_LEAKY, act_slope=0.01, out_buf=s_buf)
+    if batched:
+        dos = branches(ops.stack2(g_in, s_in, buf), 2 * B)
+        return dos[:B], dos[B:]
+    # dropout: the two branches draw their masks in the reference's order (global branch first)
+    dos_global = branches(g_in, B)
+    dos_system = branches(s_in, B)
     return dos_global, dos_system
+
+
+def gemm_weights(model):
+    """The 2-D weights that feed tensor-core GEMMs as the B operand (every live nn.Linear.weight except the H -> 1
+    out_layer, which is a streaming row-dot): the set ops.refresh_weight_planes converts once per step.  Embedding
+    tables enter as activations and the reference's dead parameters (node_mlp_1, attention projections) never run."""
+    skip = ("node_mlp_1", ".self_attn.", "embeddings", "promt_token", "prompt_token", "out_layer")
+    return [p for n, p in model.named_parameters() if p.dim() == 2 and not any(k in n for k in skip)]
 
 
 def require_cuda(t: torch.Tensor, what: str):

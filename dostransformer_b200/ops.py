@@ -129,13 +129,19 @@ class CrystalGraph:
     nmax_host: Optional[int] = None   # the same number on the host when the collate / sharder knows it (no device sync)
     _trows: dict = field(default_factory=dict)
 
-    def ragged(self):
-        """(ptr_ext, n_ext): first row and row count of every crystal in the extended key plane (atoms + 1 phantom row)."""
-        if "ragged" not in self._trows:
-            ar = torch.arange(self.B, dtype=torch.int32, device=self.row.device)
-            ptr = self.crystals.rowptr
-            self._trows["ragged"] = ((ptr[:-1] + ar).contiguous(), (ptr[1:] - ptr[:-1] + 1).contiguous())
-        return self._trows["ragged"]
+    def ragged(self, reps: int = 1):
+        """(ptr_ext, n_ext): first row and row count of every crystal in the extended key plane (atoms + 1 phantom row),
+        repeated ``reps`` times (sequence s of S = reps * B attends to crystal s % B)."""
+        key = ("ragged", reps)
+        if key not in self._trows:
+            if reps == 1:
+                ar = torch.arange(self.B, dtype=torch.int32, device=self.row.device)
+                ptr = self.crystals.rowptr
+                self._trows[key] = ((ptr[:-1] + ar).contiguous(), (ptr[1:] - ptr[:-1] + 1).contiguous())
+            else:
+                p1, n1 = self.ragged(1)
+                self._trows[key] = (p1.repeat(reps), n1.repeat(reps))
+        return self._trows[key]
 
     @property
     def ptr(self) -> torch.Tensor:
@@ -177,17 +183,20 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
     # would get a negative phantom-key count and, on the tensor-core attention path, more score columns than were
     # allocated.  The batch's own maximum is known on the host when the collate recorded it (`nmax_hint`); otherwise the
     # device value max(override, measured) is used and the host-sized tensor-core path is only taken with a hint.
-    if nmax_override is not None and nmax_hint is not None and int(nmax_override) < int(nmax_hint):
-        raise ValueError(f"max_num_nodes={int(nmax_override)} (model.max_num_nodes / sharder) is smaller than this batch's "
-                         f"largest crystal ({int(nmax_hint)} nodes): stale data-parallel padding length")
     host = None
-    if nmax_override is not None:
+    if not phantoms:
+        # per-crystal evaluation (the reference's batch_size-1 loaders): no padding, hence no phantom keys and no use for
+        # a data-parallel padding length; buffers are sized by the batch's own maximum when the collate recorded it
+        nmax = torch.zeros(1, dtype=torch.int32, device=batch.device)
+        host = int(nmax_hint) if nmax_hint is not None else None
+    elif nmax_override is not None:
+        if nmax_hint is not None and int(nmax_override) < int(nmax_hint):
+            raise ValueError(f"max_num_nodes={int(nmax_override)} (model.max_num_nodes / sharder) is smaller than this "
+                             f"batch's largest crystal ({int(nmax_hint)} nodes): stale data-parallel padding length")
         L.check(L.lib().dost_imax_scalar(L.p(nmax), int(nmax_override), L.stream()), "imax_scalar")   # nmax = max(nmax, override)
         host = int(nmax_override) if nmax_hint is not None else None
     elif nmax_hint is not None:
         host = int(nmax_hint)
-    if not phantoms:      # per-crystal evaluation (the reference's batch_size-1 loaders): no padding, hence no phantom keys
-        nmax = torch.zeros(1, dtype=torch.int32, device=batch.device)
     return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host)
 
 
@@ -341,12 +350,17 @@ def invalidate_weight_planes(model=None) -> None:
         base.__dict__.pop("_dost_weight_planes", None)
 
 
+def _planes_key(w: torch.Tensor):
+    return (w.storage_offset(), tuple(w.shape), tuple(w.stride()), _PRECISION != L.PREC_BF16)
+
+
 def weight_planes(w: torch.Tensor) -> Planes:
     """Planes of a parameter (or of a strided view of one), cached ON the parameter object until it is modified in
-    place (optimizer step).  Keying on the object - not on its address - keeps the cache exact across models."""
+    place (optimizer step).  Keying on the object - not on its address - keeps the cache exact across models.  A column
+    slice of a parameter whose full planes are cached (refresh_weight_planes) is served as a view of those."""
     base = w._base if w._base is not None else w
     cache = base.__dict__.setdefault("_dost_weight_planes", {})
-    key = (w.storage_offset(), tuple(w.shape), tuple(w.stride()), _PRECISION != L.PREC_BF16)
+    key = _planes_key(w)
     # the address too: `p.data = other` swaps storage without a version bump
     ver = (base._version, base.data_ptr(), _PLANES_GENERATION)
     hit = cache.get(key)
@@ -358,9 +372,54 @@ def weight_planes(w: torch.Tensor) -> Planes:
                 raise RuntimeError("stale weight planes: a parameter was written without bumping its version counter "
                                    "(p.data.*, raw pointers); call ops.invalidate_weight_planes(model) after such writes")
         return hit[1]
+    if base is not w and base.dim() == 2 and w.dim() == 2 and w.stride() == base.stride() and w.shape[0] == base.shape[0]:
+        full = cache.get(_planes_key(base))
+        c0 = w.storage_offset() - base.storage_offset()
+        if full is not None and full[0] == ver and 0 <= c0 < base.stride(0) and c0 % 8 == 0 and \
+                (w.shape[1] % 8 == 0 or c0 + w.shape[1] == base.shape[1]):
+            pl = cols_view(full[1], c0, c0 + w.shape[1])
+            cache[key] = (ver, pl)
+            return pl
     pl = split_planes(w.detach())
     cache[key] = (ver, pl)
     return pl
+
+
+def refresh_weight_planes(weights: Sequence[torch.Tensor]) -> None:
+    """Splits all of ``weights`` (2-D fp32 parameters) into operand planes with ONE launch per 24 tensors and fills the
+    cache of weight_planes: the once-per-step refresh after an optimizer update, and the first node of a captured step
+    (graphed.GraphedStep), where the cache cannot be trusted across replays."""
+    ws = [w for w in weights if w.dim() == 2 and w.dtype == torch.float32 and w.is_cuda and w.stride(1) == 1]
+    if not ws:
+        return
+    with_lo = _with_lo()
+    dev = ws[0].device
+    sizes = [w.shape[0] * _pad8(w.shape[1]) for w in ws]
+    offs, total = [], 0
+    for n in sizes:
+        offs.append(total)
+        total += (n + 7) // 8 * 8                   # every plane starts 16-byte aligned
+    flat_hi = torch.empty(total, dtype=torch.bfloat16, device=dev)
+    flat_lo = torch.empty(total, dtype=torch.bfloat16, device=dev) if with_lo else None
+    n = len(ws)
+    his, los = [], []
+    for w, o, sz in zip(ws, offs, sizes):
+        ldp = _pad8(w.shape[1])
+        hi = flat_hi[o:o + sz].view(w.shape[0], ldp)
+        lo = flat_lo[o:o + sz].view(w.shape[0], ldp) if with_lo else None
+        his.append(hi)
+        los.append(lo)
+    vp = lambda xs: (C.c_void_p * n)(*xs)
+    ll = lambda xs: (C.c_longlong * n)(*xs)
+    L.check(L.lib().dost_split_planes_multi(
+        n, vp([w.data_ptr() for w in ws]), ll([w.stride(0) for w in ws]), ll([w.shape[0] for w in ws]),
+        (C.c_int * n)(*[w.shape[1] for w in ws]), vp([h.data_ptr() for h in his]),
+        vp([(l.data_ptr() if l is not None else None) for l in los]), ll([_pad8(w.shape[1]) for w in ws]), L.stream()),
+        "split_planes_multi")
+    for w, hi, lo in zip(ws, his, los):
+        base = w._base if w._base is not None else w
+        cache = base.__dict__.setdefault("_dost_weight_planes", {})
+        cache[_planes_key(w)] = ((base._version, base.data_ptr(), _PLANES_GENERATION), Planes(hi, lo, w.shape[0], w.shape[1]))
 
 
 def _planes_c(pl: Planes, width: int) -> L.PlanesC:
@@ -730,6 +789,7 @@ class LinearSpec:
     act_slope: float = 0.0
     want_pre: bool = False           # also return the pre-activation / pre-residual value
     rowbias_div: int = 0             # > 0: a [M / div, N] row-group bias input follows the residual (planes path only)
+    out_buf: Optional[torch.Tensor] = None   # write the result into this [M, N] row block of a larger buffer (stack2)
 
 
 class _Linear(torch.autograd.Function):
@@ -743,7 +803,8 @@ class _Linear(torch.autograd.Function):
         N, K = weight.shape
         M = spec.M
         dev = weight.device
-        out = torch.empty(M, N, dtype=weight.dtype, device=dev)
+        out = spec.out_buf if spec.out_buf is not None else torch.empty(M, N, dtype=weight.dtype, device=dev)
+        assert out.shape == (M, N) and out.stride(1) == 1
         need_pre = spec.want_pre or spec.act == L.ACT_PRELU
         pre = torch.empty(M, N, dtype=weight.dtype, device=dev) if need_pre else None
         ctx.use_planes = _linear_on_planes(spec, weight, tensors)
@@ -1032,11 +1093,13 @@ class _RowDot(torch.autograd.Function):
 def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: torch.Tensor,
            bias: Optional[torch.Tensor], *, M: Optional[int] = None, act: int = L.ACT_NONE, act_slope: float = 0.0,
            prelu_slope: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
-           want_pre: bool = False, rowbias: Optional[torch.Tensor] = None, rowbias_div: int = 0):
+           want_pre: bool = False, rowbias: Optional[torch.Tensor] = None, rowbias_div: int = 0,
+           out_buf: Optional[torch.Tensor] = None):
     """Fused Linear.  ``segments`` are concatenated along the feature axis; a tensor may appear in several.
-    ``rowbias`` [ceil(M / rowbias_div), N] is added to row m as rowbias[m // rowbias_div] (tensor-core path only)."""
+    ``rowbias`` [ceil(M / rowbias_div), N] is added to row m as rowbias[m // rowbias_div] (tensor-core path only).
+    ``out_buf``: a [M, N] row block of a larger buffer to write the result into (see stack2)."""
     if (weight.shape[0] == 1 and len(segments) == 1 and segments[0][1] is None and act == L.ACT_NONE and residual is None
-            and not want_pre and rowbias is None and weight.dtype == torch.float32 and weight.shape[1] in (128, 256, 512)
+            and not want_pre and rowbias is None and out_buf is None and weight.dtype == torch.float32 and weight.shape[1] in (128, 256, 512)
             and weight.is_contiguous()):
         x = segments[0][0]
         if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0:
@@ -1055,8 +1118,44 @@ def linear(segments: Sequence[Tuple[torch.Tensor, Optional[RowMap]]], weight: to
         t0, m0 = segments[0]
         assert m0 is None or (m0.idx is None and m0.div == 1)
         M = t0.shape[0]
-    spec = LinearSpec([m for _, m in segments], tos, M, act, act_slope, want_pre, rowbias_div if rowbias is not None else 0)
+    spec = LinearSpec([m for _, m in segments], tos, M, act, act_slope, want_pre, rowbias_div if rowbias is not None else 0,
+                      out_buf)
     return _Linear.apply(spec, weight, bias, prelu_slope, residual, rowbias, *tensors)
+
+
+class _Box:
+    """Keeps a tensor out of autograd's sight when passed to Function.apply."""
+
+    def __init__(self, t):
+        self.t = t
+
+
+class _Stack2(torch.autograd.Function):
+    """[a; b] along the rows WITHOUT a copy: a and b are the two row blocks of ``buf`` already (their producers wrote
+    there through ``linear(out_buf=...)``).  Backward hands each producer its row block of the gradient (views)."""
+
+    @staticmethod
+    def forward(ctx, a, b, box):
+        buf = box.t
+        ra = a.shape[0]
+        assert a.data_ptr() == buf.data_ptr() and b.data_ptr() == buf[ra:].data_ptr() and ra + b.shape[0] == buf.shape[0]
+        ctx.ra = ra
+        return buf
+
+    @staticmethod
+    def backward(ctx, d):
+        return d[:ctx.ra], d[ctx.ra:], None
+
+
+def stack2_buffer(rows_a: int, rows_b: int, cols: int, like: torch.Tensor):
+    """(buf, view_a, view_b): one [rows_a + rows_b, cols] buffer and its two row blocks, to be filled by two
+    ``linear(..., out_buf=view)`` calls and then joined with ``stack2``."""
+    buf = torch.empty(rows_a + rows_b, cols, dtype=like.dtype, device=like.device)
+    return buf, buf[:rows_a], buf[rows_a:]
+
+
+def stack2(a: torch.Tensor, b: torch.Tensor, buf: torch.Tensor) -> torch.Tensor:
+    return _Stack2.apply(a, b, _Box(buf))
 
 
 # =====================================================================================================
@@ -1224,18 +1323,20 @@ class _CrossAttention(torch.autograd.Function):
 class _CrossAttentionTC(torch.autograd.Function):
     """The same attention with its contractions on the tensor cores: ragged batched GEMMs (one problem per sequence, the
     keys of its crystal addressed by a row offset into one extended key plane that carries a phantom-key row per
-    crystal), fp32 softmax in between (csrc/xattn_tc.cu).  Needs S == B, no dropout and the padding length on the host."""
+    crystal), fp32 softmax in between (csrc/xattn_tc.cu).  S = reps * B sequences (sequence s attends to crystal s % B: the
+    global and the system branch of DOSTransformer.py:71-91 batched together); needs no dropout and the padding length on
+    the host."""
 
     @staticmethod
-    def forward(ctx, q, kv, phantom, resid, graph: CrystalGraph, qpl: Optional[Planes]):
+    def forward(ctx, q, kv, phantom, resid, graph: CrystalGraph, qpl: Optional[Planes], S: int):
         N, H = kv.shape
         B = graph.B
         T = q.shape[-2]
-        S = B
+        reps = S // B
         dev = kv.device
         lib = L.lib()
         npad = _pad8(graph.nmax_host + 1)
-        ptr_ext, n_ext = graph.ragged()
+        ptr_ext, n_ext = graph.ragged(reps)
         q, resid = q.contiguous(), resid.contiguous()
         bcast_q = q.dim() == 2
         if bcast_q:                       # first layer of the first stack: every crystal shares the energy embeddings
@@ -1261,7 +1362,7 @@ class _CrossAttentionTC(torch.autograd.Function):
                     b_rowoff=ptr_ext)
         ctx.save_for_backward(kv, phantom, scores, lse, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
         ctx.graph, ctx.prec, ctx.npad = graph, _PRECISION, npad
-        ctx.bcast_q, ctx.bcast_r, ctx.T = bcast_q, resid.dim() == 2, T
+        ctx.bcast_q, ctx.bcast_r, ctx.T, ctx.S = bcast_q, resid.dim() == 2, T, S
         return out
 
     @staticmethod
@@ -1270,11 +1371,12 @@ class _CrossAttentionTC(torch.autograd.Function):
         g: CrystalGraph = ctx.graph
         N, H = kv.shape
         B, T, npad = g.B, ctx.T, ctx.npad
-        S = B
+        S = ctx.S
+        reps = S // B
         dev = kv.device
         lib = L.lib()
         with precision_value(ctx.prec):
-            ptr_ext, n_ext = g.ragged()
+            ptr_ext, n_ext = g.ragged(reps)
             qp, kvp, pp = Planes(qh, ql, S * T, H), Planes(kh, kl, N + B, H), Planes(ph, pl_, S * T, npad)
             d_out = d_out.contiguous()
             dop = split_planes(d_out.view(S * T, H))
@@ -1290,11 +1392,15 @@ class _CrossAttentionTC(torch.autograd.Function):
             gemm_planes(M=T, N=H, K=npad, a=[dsp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=dq.view(S * T, H), batch=S,
                         a_bstride=T * dsp.ld, c_bstride=T * H, b_rowoff=ptr_ext)
             # d(extended keys) = dS^T q + P^T dO, written at each crystal's rows of the extended plane
+            # (sequences s and s + B write the same crystal's rows: one launch per repetition, accumulating in order)
             dext = torch.empty(N + B, H, dtype=torch.float32, device=dev)
-            gemm_planes(M=npad, N=H, K=T, a=[dsp], a_mode=L.MC, b=qp, b_mode=L.MC, out=dext, batch=S, a_bstride=T * dsp.ld,
-                        b_bstride=T * qp.ld, c_rowoff=ptr_ext, c_rowlim=n_ext)
-            gemm_planes(M=npad, N=H, K=T, a=[pp], a_mode=L.MC, b=dop, b_mode=L.MC, out=dext, accumulate=True, batch=S,
-                        a_bstride=T * pp.ld, b_bstride=T * dop.ld, c_rowoff=ptr_ext, c_rowlim=n_ext)
+            p1, n1 = g.ragged(1)
+            for rep in range(reps):
+                r0, r1 = rep * B * T, (rep + 1) * B * T
+                gemm_planes(M=npad, N=H, K=T, a=[_rows(dsp, r0, r1)], a_mode=L.MC, b=_rows(qp, r0, r1), b_mode=L.MC, out=dext,
+                            accumulate=rep > 0, batch=B, a_bstride=T * dsp.ld, b_bstride=T * qp.ld, c_rowoff=p1, c_rowlim=n1)
+                gemm_planes(M=npad, N=H, K=T, a=[_rows(pp, r0, r1)], a_mode=L.MC, b=_rows(dop, r0, r1), b_mode=L.MC, out=dext,
+                            accumulate=True, batch=B, a_bstride=T * pp.ld, b_bstride=T * dop.ld, c_rowoff=p1, c_rowlim=n1)
             dkv = torch.empty(N, H, dtype=torch.float32, device=dev)
             dbrows = torch.empty(B, H, dtype=torch.float32, device=dev)
             L.check(lib.dost_xattn_kv_ext_split(L.p(dext), L.p(g.batch), L.p(g.ptr), N, B, H, L.p(dkv), L.p(dbrows), L.stream()),
@@ -1302,14 +1408,20 @@ class _CrossAttentionTC(torch.autograd.Function):
             dph = colsum(dbrows)
             d_q = colsum(dq.view(S, T * H)).view(T, H) if ctx.bcast_q else dq
             d_resid = colsum(d_out.view(S, T * H)).view(T, H) if ctx.bcast_r else d_out
-        return d_q, dkv, dph, d_resid, None, None
+        return d_q, dkv, dph, d_resid, None, None, None
+
+
+def _rows(pl: Planes, r0: int, r1: int) -> Planes:
+    """Row range [r0, r1) of an operand (a view)."""
+    return Planes(pl.hi[r0:r1], pl.lo[r0:r1] if pl.lo is not None else None, r1 - r0, pl.cols)
 
 
 def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float = 0.0, seed: int = 0):
     H = kv.shape[1]
-    if (tc_active(kv) and H % 128 == 0 and drop_p == 0.0 and S == graph.B and graph.nmax_host is not None
-            and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")):
-        return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q))
+    if (tc_active(kv) and H % 128 == 0 and drop_p == 0.0 and S % graph.B == 0 and graph.nmax_host is not None
+            and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")
+            and (q.dim() == 3 or S == graph.B)):
+        return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q), S)
     return _CrossAttention.apply(q, kv, phantom, resid, graph, S, drop_p, seed)
 
 

@@ -172,6 +172,11 @@ typedef struct {
 
 size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g);
 int dost_gemm_bf16(const dost_gemm_bf16_t* g, void* workspace, size_t workspace_bytes, dost_stream_t stream);
+/* The same conversion for `ntensors` matrices in one launch per 24 (host arrays of per-tensor pointers / sizes; the
+ * descriptors travel in the kernel parameters).  Refreshes the operand planes of all Linear weights once per step
+ * (nn.Linear.weight in DOSTransformer.py:103-105,171,182, layers/transformer.py:114-115); lo[i] may be NULL. */
+int dost_split_planes_multi(int ntensors, const float* const* x, const long long* ld, const long long* rows, const int* cols,
+                            void* const* hi, void* const* lo, const long long* ldp, dost_stream_t stream);
 /* fp32 [rows, cols] (ld) -> bf16 planes [rows, ldp] (ldp % 8 == 0, columns >= cols zero-filled); lo may be NULL. */
 int dost_split_planes(const float* x, long long ld, long long rows, int cols, void* hi, void* lo, long long ldp,
                       dost_stream_t stream);

@@ -1,9 +1,9 @@
-"""Import the reference's own model code, unchanged, from /root/reference.
+"""Import the reference's own model code, unchanged, from /root/reference or from its staged copy oracle/_ref/.
 
-TEST INFRASTRUCTURE ONLY.  Works only in the build container (the GPU box has
-no /root/reference); used by oracle/make_golden.py to generate tests/golden/
-and by the ``not gpu`` tests that pin oracle/dost_oracle.py against the live
-reference when it is present.
+TEST INFRASTRUCTURE ONLY.  /root/reference exists only in the build container; oracle/build_ref.py stages the files of
+the hot path under oracle/_ref/ (git-ignored, travels to the GPU box with the snapshot), byte-for-byte.  Used by
+oracle/make_golden.py to generate tests/golden/, by the ``not gpu`` tests that pin oracle/dost_oracle.py against the
+live reference, and by bench.py's CPU legs (``--impl reference`` / ``cpu_baseline``, kind "reference").
 """
 from __future__ import annotations
 
@@ -13,7 +13,20 @@ import sys
 
 from . import shims
 
-REFERENCE_ROOT = os.environ.get("DOST_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("DOST_REFERENCE_ROOT")
+    if env:
+        return env
+    for root in ("/root/reference", _STAGED):
+        if os.path.isfile(os.path.join(root, "embedder_eDOS", "DOSTransformer.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 _CACHE = {}
 
 

@@ -34,12 +34,14 @@ def main():
     for _ in range(2):                              # twice: the reduced gradients must be bit-identical across runs
         model.zero_grad(set_to_none=True)
         dg, x, ds = model(mine)
-        loss = ops.dos_loss(dg, ds, mine.y_ft, mode="edos", beta=1.0) * weights[rank]
-        loss.backward()
+        loss_t = ops.dos_loss(dg, ds, mine.y_ft, mode="edos", beta=1.0) * weights[rank]
+        loss_t.backward()
+        loss = float(loss_t)
         reducer.finish()
         torch.cuda.synchronize()
         runs.append({k: p.grad.detach().cpu().clone() for k, p in dp.live_named_parameters(model)})
     reducer.remove()
+    del dg, x, ds, loss_t
     # the graph-replay step (flat all-reduce after the replay) must give the same reduced gradients
     step = GraphedStep(model, "edos", loss_weight=weights[rank], world=world)
     step(mine)

@@ -15,8 +15,11 @@ from dostransformer_b200.synthetic import make_edos_batch
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # rel-L2 per tensor between the 2-rank and the 1-rank gradients: both are the same math with a different summation
-# grouping (per-rank partial sums, then one addition), so only rounding differs
-TOL = {"fp32": 2e-5, "bf16x3": 1e-4}
+# grouping (per-rank partial sums, then one addition), so only rounding differs.  fp32 path: fp32 rounding.  bf16x3: the
+# stated gradient floor of that path (tests/test_gpu_model.py GRAD_FLOOR): the tensor-core
+# accumulation order moves with the split-K chunking, and the cancellation-prone first-stack gradients
+# (embeddings.weight, transformer.layers.*.fc1: 1e-3 measured) amplify it exactly as they amplify the bf16x3-vs-fp64 error
+TOL = {"fp32": 2e-5, "bf16x3": 2e-3}
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

@@ -884,3 +884,61 @@ def test_planes_gemm_batched_and_ragged(prec, tol):
             ref = p[z, :, :n[z]].double().T @ q[z].double()
             got = dk[off[z]:off[z] + n[z]].double()
             assert (got - ref).abs().max() / ref.abs().max() < tol, z
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,N,K,b_mode", [(256, 256, 256, "KC"), (1000, 512, 768, "KC"), (333, 72, 200, "KC"), (4100, 1024, 256, "MC"),
+                                          (130, 260, 64, "KC"), (5000, 256, 1024, "MC"), (77, 40, 48, "KC"), (32, 32, 64, "KC")])
+def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, b_mode, monkeypatch):
+    """The TMA-store epilogue (values finished in the accumulator layout, staged in the TMA swizzle, cp.async.bulk.tensor
+    stores; csrc/gemm_bf.cu) must reproduce the register epilogue BIT FOR BIT: same accumulators, same fp32 operations per
+    element (bias, row-group bias, activation, act' mask, residual, bf16 hi/lo split); ragged M / N tails are clipped by
+    the tensor map.  Column sums (bias gradients) are summed in a different fixed order: compared at 1e-6."""
+    torch.manual_seed(M * 7 + N + K)
+    bm = L.KC if b_mode == "KC" else L.MC
+    a = torch.randn(M, K, device=DEV)
+    w = torch.randn((N, K) if bm == L.KC else (K, N), device=DEV)
+    bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
+    rb = torch.randn((M + 6) // 7, N, device=DEV)
+    saved = torch.randn(M, N, device=DEV)
+
+    def run(tma):
+        monkeypatch.setenv("DOST_GEMM_TMA_EPI", "1" if tma else "0")
+        outs = {}
+        with ops.precision(prec):
+            ap, wp, sp = ops.split_planes(a), ops.split_planes(w), ops.split_planes(saved)
+            lo = prec != "bf16"
+            # (1) fp32 store: bias + row-group bias + LeakyReLU + residual
+            o1 = torch.full((M, N), float("nan"), device=DEV)
+            ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, out=o1, bias=bias, rowbias=rb, rowbias_div=7,
+                            act=L.ACT_LEAKY, act_slope=0.01, residual=res)
+            outs["fp32"] = o1
+            # (2) planes store: bias + ReLU (the FFN's fc1 forward)
+            p2 = ops.empty_planes(M, N, DEV, with_lo=lo)
+            p2.hi.fill_(float("nan"))
+            ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, bias=bias, act=L.ACT_RELU, out_planes=p2)
+            outs["hi"], outs["lo"] = p2.hi[:, :N], (p2.lo[:, :N] if lo else None)
+            # (3) planes store with the act' mask and the fused column sums (the FFN's fc2 input gradient)
+            p3 = ops.empty_planes(M, N, DEV, with_lo=lo)
+            cs = torch.empty(N, device=DEV)
+            ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, dact=sp, dact_slope=0.0, out_planes=p3, colsum_out=cs)
+            outs["hi3"], outs["lo3"], outs["colsum"] = p3.hi[:, :N], (p3.lo[:, :N] if lo else None), cs
+            # (4) a strided fp32 destination (a column block of a wider matrix, as the edge block's node terms)
+            wide = torch.zeros(M, 2 * N + 8, device=DEV)
+            ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, out=wide[:, N:2 * N])
+            outs["wide"] = wide
+        torch.cuda.synchronize()
+        return outs
+
+    reg, tma = run(False), run(True)
+    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide"):
+        if reg[k] is None:
+            continue
+        assert not torch.isnan(tma[k].float()).any(), k
+        assert torch.equal(reg[k], tma[k]), k
+    ref = reg["colsum"].double()
+    assert (tma["colsum"].double() - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1e-6)
+    want = (a.double() @ (w.double().T if bm == L.KC else w.double())) * torch.where(saved > 0, 1.0, 0.0).double()
+    if prec == "bf16x3":
+        assert (tma["colsum"].double() - want.sum(0)).abs().max() / want.sum(0).abs().max() < 1e-3

@@ -7,7 +7,7 @@ import re
 import pytest
 import torch
 
-from conftest import ROOT, load_golden
+from conftest import ROOT, load_golden, relerr
 from dostransformer_b200 import _lib
 from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
 from dostransformer_b200.embedder_phDOS.DOSTransformer_phonon import DOSTransformer_phonon
@@ -236,9 +236,61 @@ def test_bench_reference_arm_contract_and_product_arm_needs_gpu():
                 "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "crystals/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["vs_baseline"] is None and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # kind "reference" = the reference's own modules (/root/reference here, oracle/_ref on the GPU box); "port" = the oracle
+    from oracle import reference_loader
+    want_kind = "reference" if reference_loader.available() else "port"
+    assert d["vs_baseline"] is None and d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
     if not torch.cuda.is_available():
         r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0"],
                            capture_output=True, text=True, timeout=300, cwd=ROOT)
         assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_bucket_padding_is_a_semantic_no_op_for_the_real_crystals():
+    """synthetic.pad_edos_batch (the shape bucketing behind graphed.GraphedStep): on the CPU oracle, the padded batch's
+    outputs, loss over the first n_valid crystals and gradients equal those of the unpadded batch (the padding length
+    Nmax, which sets every crystal's phantom-key count, is unchanged because no dummy is larger than a real crystal)."""
+    from dostransformer_b200.graphed import batch_signature
+    from dostransformer_b200.synthetic import pad_edos_batch
+    from oracle import dost_oracle as O
+    torch.manual_seed(0)
+    sd = O.state_dict_of(DOSTransformer(2, 1, 200, 41, 2, 32, "cpu", 0.0))
+    g = make_edos_batch(5, seed=8, mean_atoms=6.0)
+    p = pad_edos_batch(g, node_bucket=32, dummies=2)
+    B = 5
+    assert p.n_valid == B and p.x.shape[0] % 32 == 0 and p.edge_index.shape[1] == 12 * (p.x.shape[0] - p.system.numel())
+    n = torch.bincount(p.batch)
+    assert n.min() >= 2 and int(n[B:].max()) <= int(n[:B].max())
+    leaf = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    dg, x, ds = O.edos_forward(leaf, g, training=True)
+    loss = O.edos_loss(dg, ds, g.y_ft)
+    loss.backward()
+    leaf_p = {k: (v.detach().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    dgp, xp, dsp = O.edos_forward(leaf_p, p, training=True)
+    loss_p = O.edos_loss(dgp[:B], dsp[:B], p.y_ft.reshape(-1, 201)[:B].reshape(-1))
+    loss_p.backward()
+    assert relerr(dgp[:B], dg) < 1e-5 and relerr(dsp[:B], ds) < 1e-5 and relerr(xp[:x.shape[0]], x) < 1e-5
+    assert abs(loss_p.item() - loss.item()) < 1e-6 * abs(loss.item())
+    for k, v in leaf.items():
+        if torch.is_tensor(v) and v.requires_grad and v.grad is not None:
+            assert leaf_p[k].grad is not None
+            err = ((leaf_p[k].grad - v.grad).norm() / v.grad.norm().clamp_min(1e-30)).item()
+            assert err < 5e-4, (k, err)
+    # a handful of signatures for many batches
+    sigs = {batch_signature(pad_edos_batch(make_edos_batch(64, seed=100 + s))) for s in range(12)}
+    assert len(sigs) <= 6
+
+
+def test_staged_reference_copy_is_byte_identical():
+    """oracle/build_ref.py stages the reference's model files for the GPU box: same bytes as /root/reference."""
+    import hashlib
+    import json
+    from oracle import build_ref
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference not present")
+    dst = build_ref.build()
+    man = json.load(open(os.path.join(dst, "MANIFEST.json")))
+    for rel, sha in man["sha256"].items():
+        with open(os.path.join("/root/reference", rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == sha, rel
