@@ -236,6 +236,11 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(src)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2),
+               "r"(src)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -483,6 +488,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     for (int tile = tile0; tile < p.total_tiles; tile += tile_step, ++local) {
       const TileInfo t = tile_info<BN, CTA2>(p, tile, rank);
       const int buf = local & 1;
+      // TMA-store epilogue: the side inputs of a chunk (residual, act' mask) do not depend on the accumulator.  They are
+      // requested one chunk ahead - the first chunk's before this warp even waits for the MMAs of the tile - so their DRAM
+      // latency (~1-2 us under load, once per chunk per warp otherwise) hides behind the wait and the previous chunk.
+      uint4 pre[8];        // one buffer for both kinds (a launch has a residual OR an act' mask on this path, never both)
+      const int mrow_t = t.m0 + quad * 32 + lane;
+      const long long zres = (p.zmode == 1) ? (long long)t.z * p.res_bstride : 0;
+      auto prefetch_side = [&](int c0n) {
+        const int n0 = t.n0 + half * CH + c0n;
+        const bool ok = mrow_t < Mv;
+        if (feat & F_RES) {
+          const float* rp = res_v + zres + (long long)mrow_t * ldres_v + n0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pre[j] = ldg128u_nc_if(rp + 4 * j, ok && n0 + 4 * j < Nv);
+        } else if (feat & F_DACT) {
+          const __nv_bfloat16* dp = p.dact_hi + (long long)mrow_t * p.ld_dact + n0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pre[j] = ldg128u_nc_if(dp + 8 * j, ok && n0 + 8 * j < Nv);
+        }
+      };
+      if ((feat & F_TMA) && (feat & (F_RES | F_DACT))) prefetch_side(0);
       mbar_wait(accf0 + 8 * buf, acc_phase[buf]);
       acc_phase[buf] ^= 1;
       tc_fence_after();
@@ -505,12 +530,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         for (int c0 = 0; c0 < CH; c0 += 32) {
           const int n0 = t.n0 + half * CH + c0;            // first column of the chunk (warp-uniform)
           const bool live = warp_rows_ok && n0 < Nv;
-          uint4 sg[4];
-          if ((feat & F_DACT) && live) {                   // activation-derivative mask: 32 bf16 of this thread's row
-            const __nv_bfloat16* dp = p.dact_hi + (long long)mrow * p.ld_dact + n0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sg[j] = ldg128u_nc_if(dp + 8 * j, row_ok && n0 + 8 * j < Nv);
-          }
+
           tmem_ld_wait();
           float v[32];
 #pragma unroll
@@ -549,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             const float ds = p.dact_slope;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {sg[j].x, sg[j].y, sg[j].z, sg[j].w};
+              const uint32_t w[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
                 const float m0 = __uint_as_float(w[q] << 16), m1 = __uint_as_float(w[q] & 0xFFFF0000u);
@@ -559,13 +579,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             }
           }
           if (feat & F_RES) {
-            const float* rp = res_v + (long long)mrow * ldres_v + n0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 q = ldg128_nc_if(rp + 4 * j, row_ok && n0 + 4 * j < Nv);
-              v[4 * j] += q.x; v[4 * j + 1] += q.y; v[4 * j + 2] += q.z; v[4 * j + 3] += q.w;
+              v[4 * j] += __uint_as_float(pre[j].x); v[4 * j + 1] += __uint_as_float(pre[j].y);
+              v[4 * j + 2] += __uint_as_float(pre[j].z); v[4 * j + 3] += __uint_as_float(pre[j].w);
             }
           }
+          // `pre` is consumed: the next chunk's side inputs fly during the staging / store of this chunk and the first
+          // half of the next one (no second buffer: 168 registers per thread is the ceiling with 10 warps per CTA)
+          if ((feat & (F_RES | F_DACT)) && c0 + 32 < CH) prefetch_side(c0 + 32);
           // the previous chunk's store must have finished READING the staging tile before it is overwritten
           if (lane == 0) bulk_wait_read0();
           __syncwarp();
@@ -599,11 +621,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           __syncwarp();
           if (lane == 0) {
             const int mw = t.m0 + quad * 32;
+            const int zc = (p.zmode == 1) ? t.z : 0;      // batched: the box never spans two problems (rows >= M clipped)
             if (feat & F_OUT) {
-              tma_store_2d(&maps.c_out, stg, n0, mw);
+              tma_store_3d(&maps.c_out, stg, n0, mw, zc);
             } else {
-              tma_store_2d(&maps.c_hi, stg, n0, mw);
-              if (feat & F_LO) tma_store_2d(&maps.c_lo, stg + 2048, n0, mw);
+              tma_store_3d(&maps.c_hi, stg, n0, mw, zc);
+              if (feat & F_LO) tma_store_3d(&maps.c_lo, stg + 2048, n0, mw, zc);
             }
             bulk_commit();
           }
@@ -664,11 +687,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           v[i][0] = q.x; v[i][1] = q.y; v[i][2] = q.z; v[i][3] = q.w;
         }
         __syncwarp();                                      // staging tile may be overwritten by the next chunk
-        if (n >= Nv || t.m0 + quad * 32 >= Mv) continue;    // N % 4 == 0: a thread's 4 columns are all in or all out
+        // warp-uniform skip only (the column sums below shuffle across the whole warp); a thread whose 4 columns lie past
+        // N (N % 4 == 0: all in or all out) stays in the loop with every access predicated off
+        if (t.n0 + half * CH + c0 >= Nv || t.m0 + quad * 32 >= Mv) continue;
         bool mok[8];
         const int mlim = (feat & F_ROWLIM) ? min(Mv, __ldg(p.c_rowlim + t.z)) : Mv;
+        const bool nok = n < Nv;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) mok[i] = mbase + 4 * i < mlim;
+        for (int i = 0; i < 8; ++i) mok[i] = nok && mbase + 4 * i < mlim;
         if (feat & F_SPLITK) {
           float* ws = p.ws + ((long long)t.z * Mv + mbase) * Nv + n;
           const bool empty = t.nkt == 0;                    // an empty K slice contributes zeros (its TMEM is stale)
@@ -767,7 +793,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
             cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
           }
-          if (lane < 8)
+          if (lane < 8 && nok)
             *reinterpret_cast<float4*>(p.colpart + (long long)((t.m0 + quad * 32) >> 5) * p.N + n) = make_float4(cs[0], cs[1], cs[2], cs[3]);
         }
       }
@@ -1042,19 +1068,25 @@ static int make_map(CUtensorMap* m, const void* base, long long inner, long long
   return DOST_OK;
 }
 
-// 2-D output map for the TMA-store epilogue: [outer rows][inner elements contiguous], row pitch ld elements, box {32, 32}.
-static int make_out_map(CUtensorMap* m, const void* base, bool is_f32, long long inner, long long outer, long long ld) {
+// Output map for the TMA-store epilogue: [batch][outer rows][inner elements contiguous], row pitch ld and batch pitch
+// bstride elements, box {32, 32, 1} (a box never spans two problems of a batch).
+static int make_out_map(CUtensorMap* m, const void* base, bool is_f32, long long inner, long long outer, long long ld,
+                        long long batch = 1, long long bstride = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("gemm_bf16: cuTensorMapEncodeTiled is not available");
     return DOST_ERR_UNSUPPORTED;
   }
   const int esz = is_f32 ? 4 : 2;
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
-  cuuint32_t box[2] = {32u, 32u};
-  cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+  if (batch <= 1 || bstride <= 0) {
+    batch = 1;
+    bstride = outer * ld;
+  }
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)bstride * esz};
+  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1276,12 +1308,12 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   maps.c_out = maps.b_hi;
   maps.c_hi = maps.b_hi;
   maps.c_lo = maps.b_hi;
-  if (tma_epi_enabled() && split == 1 && batch == 1 && !h->out_pre && !h->accumulate && !p.c_rowoff && !p.c_rowlim &&
-      ((h->out != nullptr) != (h->out_hi != nullptr)) && h->M >= 32 && h->N >= 32 &&
+  if (tma_epi_enabled() && split == 1 && !h->out_pre && !h->accumulate && !p.c_rowoff && !p.c_rowlim &&
+      ((h->out != nullptr) != (h->out_hi != nullptr)) && h->M >= 32 && h->N >= 32 && !(h->dact_hi && h->residual) &&
       (!h->dact_hi || (al16(h->dact_hi) && h->ld_dact % 8 == 0))) {
     int rc2 = DOST_OK;
-    if (h->out) {
-      rc2 = make_out_map(&maps.c_out, h->out, true, h->N, h->M, h->ldc);
+    if (h->out) {     // (batched problems: fp32 stores only, checked above)
+      rc2 = make_out_map(&maps.c_out, h->out, true, h->N, h->M, h->ldc, batch, h->c_bstride);
     } else if (al16(h->out_hi) && al16(h->out_lo) && h->ld_op % 8 == 0) {
       rc2 = make_out_map(&maps.c_hi, h->out_hi, false, h->N, h->M, h->ld_op);
       if (rc2 == DOST_OK && h->out_lo) rc2 = make_out_map(&maps.c_lo, h->out_lo, false, h->N, h->M, h->ld_op);

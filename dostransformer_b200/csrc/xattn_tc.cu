@@ -73,12 +73,26 @@ __global__ void __launch_bounds__(256) kv_ext_split_kernel(const float* __restri
     *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(dext + src * H + c));
 }
 
-// one warp per (sequence, query) row; NPL = ceil(npad / 32) columns per lane
+// Number of the nph = nmax - nb phantom copies of row r that survive dropout (warp-cooperative; the copies occupy the key
+// slots nb .. nmax-1 of the padded row, the mask index convention of attention_v2.cu: idx = r * nmax + key slot).
+__device__ __forceinline__ int phantom_kept(unsigned long long seed, long long r, int nb, int nmax, unsigned int thresh, int lane) {
+  int kept = 0;
+  for (int jj = nb + lane; jj < nmax; jj += 32)
+    kept += keep_mask(seed, (unsigned long long)r * (unsigned long long)nmax + jj, thresh) ? 1 : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  return kept;
+}
+
+// one warp per (sequence, query) row; NPL = ceil(npad / 32) columns per lane.  Dropout (thresh != 0): the planes receive
+// the dropped-out probabilities mask / (1 - p) * P (multiheaded_attention.py:71); the phantom column carries
+// (surviving copies) / (1 - p) * P_phantom.
 template <int NPL>
 __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ sc, const int* __restrict__ ptr,
                                                           const int* __restrict__ nmax_p, long long rows, int B, int Tn, int npad,
                                                           float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                          long long ldp, float* __restrict__ lse, unsigned int* __restrict__ errw) {
+                                                          long long ldp, float* __restrict__ lse, unsigned int* __restrict__ errw,
+                                                          unsigned int thresh, float inv_keep, unsigned long long seed) {
   const int lane = threadIdx.x & 31;
   const int nmax = *nmax_p;
   for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
@@ -104,17 +118,20 @@ __global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restric
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + 32 * i;
       float e = (c < ncol) ? expf(v[i] - mx) : 0.f;
-      if (c == nb) e *= (float)nph;               // the phantom column stands for nph identical keys
+      sum += (c == nb) ? e * (float)nph : e;      // the phantom column stands for nph identical keys
       v[i] = e;
-      sum += e;
     }
     sum = warp_sum(sum);
     const float inv = 1.0f / sum;
+    float wph = (float)nph;                        // weight of the phantom column: surviving copies / (1 - p)
+    if (thresh && nph > 0) wph = (float)phantom_kept(seed, r, nb, nmax, thresh, lane) * inv_keep;
 #pragma unroll
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + 32 * i;
       if (c < ldp) {
-        const float p = v[i] * inv;               // zero for masked columns
+        float p = v[i] * inv;                     // zero for masked columns
+        if (c == nb) p *= wph;
+        else if (thresh && c < nb) p = keep_mask(seed, (unsigned long long)r * (unsigned long long)nmax + c, thresh) ? p * inv_keep : 0.f;
         const __nv_bfloat16 h = __float2bfloat16_rn(p);
         hi[r * ldp + c] = h;
         if (lo) lo[r * ldp + c] = __float2bfloat16_rn(p - __bfloat162float(h));
@@ -129,7 +146,7 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
                                                           const float* __restrict__ dP, const int* __restrict__ ptr,
                                                           const int* __restrict__ nmax_p, long long rows, int B, int Tn, int npad,
                                                           float scale, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                                          long long ldp) {
+                                                          long long ldp, unsigned int thresh, float inv_keep, unsigned long long seed) {
   const int lane = threadIdx.x & 31;
   const int nmax = *nmax_p;
   for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
@@ -138,6 +155,10 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     const int nph = max(nmax - nb, 0);
     const int ncol = nb + (nph > 0 ? 1 : 0);
     const float ls = __ldg(lse + r);
+    float wph = (float)nph;                        // sum over the phantom copies of mask / (1 - p)
+    if (thresh && nph > 0) wph = (float)phantom_kept(seed, r, nb, nmax, thresh, lane) * inv_keep;
+    // p: probability of ONE key (one phantom copy); g: gradient wrt its dropped-out probability, already weighted by the
+    // mask (real keys) or by the surviving copies (phantom column)
     float p[NPL], g[NPL];
     float dot = 0.f;
 #pragma unroll
@@ -146,9 +167,12 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
       p[i] = 0.f;
       g[i] = 0.f;
       if (c < ncol) {
-        p[i] = expf(sc[r * npad + c] * scale - ls) * (c == nb ? (float)nph : 1.f);
-        g[i] = dP[r * npad + c];
-        dot = fmaf(p[i], g[i], dot);
+        p[i] = expf(sc[r * npad + c] * scale - ls);
+        float gv = dP[r * npad + c];
+        if (c == nb) gv *= wph;
+        else if (thresh) gv = keep_mask(seed, (unsigned long long)r * (unsigned long long)nmax + c, thresh) ? gv * inv_keep : 0.f;
+        g[i] = gv;
+        dot = fmaf(p[i], gv, dot);
       }
     }
     dot = warp_sum(dot);
@@ -156,7 +180,8 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
     for (int i = 0; i < NPL; ++i) {
       const int c = lane + 32 * i;
       if (c < ldp) {
-        const float o = scale * p[i] * (g[i] - dot);
+        // d(score) summed over the copies a column stands for: real key p (g - dot); phantom p (wph g_raw - nph dot)
+        const float o = scale * p[i] * (g[i] - ((c == nb) ? (float)nph : 1.f) * dot);
         const __nv_bfloat16 h = __float2bfloat16_rn(o);
         hi[r * ldp + c] = h;
         if (lo) lo[r * ldp + c] = __float2bfloat16_rn(o - __bfloat162float(h));
@@ -204,24 +229,31 @@ static inline int npl_for(long long ldp) {
 }
 
 extern "C" int dost_xattn_softmax_fwd(const float* scores, const int32_t* ptr, const int32_t* nmax, long long rows, int B, int T,
-                                      int npad, double scale, void* hi, void* lo, long long ldp, float* lse, dost_stream_t stream) {
+                                      int npad, double scale, void* hi, void* lo, long long ldp, float* lse, double drop_p,
+                                      unsigned long long seed, dost_stream_t stream) {
   DOST_REQUIRE(scores && ptr && nmax && hi && lse && rows > 0 && npad > 0 && ldp >= npad && ldp <= 1024, "xattn_softmax_fwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   const int npl = npl_for(ldp);
   const int blocks = (int)min64((rows + 7) / 8, 32LL * kNumSMs);
+  DOST_REQUIRE(drop_p >= 0.0 && drop_p < 1.0, "xattn_softmax_fwd: drop_p must be in [0, 1)");
+  const unsigned int thresh = drop_p > 0.0 ? drop_threshold(drop_p) : 0u;
+  const float inv_keep = (float)(1.0 / (1.0 - drop_p));
   DOST_XTC_DISPATCH(softmax_fwd_kernel, scores, ptr, nmax, rows, B, T, npad, (float)scale, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp, lse,
-                    device_error_words())
+                    device_error_words(), thresh, inv_keep, seed)
   return check_launch("xattn_softmax_fwd");
 }
 
 extern "C" int dost_xattn_softmax_bwd(const float* scores, const float* lse, const float* dP, const int32_t* ptr, const int32_t* nmax,
                                       long long rows, int B, int T, int npad, double scale, void* hi, void* lo, long long ldp,
-                                      dost_stream_t stream) {
+                                      double drop_p, unsigned long long seed, dost_stream_t stream) {
   DOST_REQUIRE(scores && lse && dP && ptr && nmax && hi && rows > 0 && npad > 0 && ldp >= npad && ldp <= 1024, "xattn_softmax_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   const int npl = npl_for(ldp);
   const int blocks = (int)min64((rows + 7) / 8, 32LL * kNumSMs);
+  DOST_REQUIRE(drop_p >= 0.0 && drop_p < 1.0, "xattn_softmax_bwd: drop_p must be in [0, 1)");
+  const unsigned int thresh = drop_p > 0.0 ? drop_threshold(drop_p) : 0u;
+  const float inv_keep = (float)(1.0 / (1.0 - drop_p));
   DOST_XTC_DISPATCH(softmax_bwd_kernel, scores, lse, dP, ptr, nmax, rows, B, T, npad, (float)scale, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo,
-                    ldp)
+                    ldp, thresh, inv_keep, seed)
   return check_launch("xattn_softmax_bwd");
 }

@@ -182,8 +182,13 @@ class GradReducer:
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._work[bi] = (flat, work)
 
-    def finish(self) -> None:
-        """Wait for every bucket (launching any that never completed, e.g. unused parameters) and write back."""
+    def finish(self, optimizer=None) -> None:
+        """Wait for every bucket (launching any that never completed, e.g. unused parameters) and write the reduced
+        values back into ``p.grad``.
+
+        optimizer (a dostransformer_b200.optim.AdamW): fuse the optimizer into the all-reduce epilogue instead - bucket i
+        is updated straight from its reduced flat buffer on the reducer's stream as soon as its reduction has completed,
+        while buckets i+1.. are still being reduced; nothing is copied back (``p.grad`` keeps the LOCAL gradient)."""
         for bi, b in enumerate(self.buckets):
             if self._work[bi] is None:
                 have = [p for p in b if p.grad is not None]
@@ -201,7 +206,12 @@ class GradReducer:
                     if self.average:
                         flat.div_(world)
                     gl = [p.grad for p in b]
-                    torch._foreach_copy_(gl, list(torch._utils._unflatten_dense_tensors(flat, gl)))   # one launch per bucket
+                    views = list(torch._utils._unflatten_dense_tensors(flat, gl))
+                    if optimizer is not None:
+                        optimizer.step_subset(list(b), views)
+                        flat.record_stream(self._stream)
+                    else:
+                        torch._foreach_copy_(gl, views)   # one launch per bucket
             else:
                 work.wait()
                 if self.average:

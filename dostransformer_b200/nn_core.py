@@ -191,7 +191,7 @@ def dos_heads(model, x_nodes, graph: ops.CrystalGraph, graph_vec, prompt_table, 
     # The global and the system branch share transformer_self / transformer_source / out_layer
     # (DOSTransformer.py:71-77 vs :85-91): they run as ONE batch of 2B sequences - half the launches, twice the rows per
     # GEMM, and the shared weights receive one gradient instead of two that autograd would have to add.
-    batched = seeds.p == 0.0 and not L.switch("DOST_NO_BRANCH_BATCH")
+    batched = not L.switch("DOST_NO_BRANCH_BATCH")     # (dropout: one mask stream per attention call, indexed by sequence)
     buf = g_buf = s_buf = None
     if batched:
         buf, g_buf, s_buf = ops.stack2_buffer(B * T, B * T, H, e2d)
@@ -215,7 +215,6 @@ def dos_heads(model, x_nodes, graph: ops.CrystalGraph, graph_vec, prompt_table, 
     if batched:
         dos = branches(ops.stack2(g_in, s_in, buf), 2 * B)
         return dos[:B], dos[B:]
-    # dropout: the two branches draw their masks in the reference's order (global branch first)
     dos_global = branches(g_in, B)
     dos_system = branches(s_in, B)
     return dos_global, dos_system

@@ -1324,11 +1324,11 @@ class _CrossAttentionTC(torch.autograd.Function):
     """The same attention with its contractions on the tensor cores: ragged batched GEMMs (one problem per sequence, the
     keys of its crystal addressed by a row offset into one extended key plane that carries a phantom-key row per
     crystal), fp32 softmax in between (csrc/xattn_tc.cu).  S = reps * B sequences (sequence s attends to crystal s % B: the
-    global and the system branch of DOSTransformer.py:71-91 batched together); needs no dropout and the padding length on
-    the host."""
+    global and the system branch of DOSTransformer.py:71-91 batched together); attention dropout is applied by the softmax
+    kernel when it writes the probability planes.  Needs the padding length on the host."""
 
     @staticmethod
-    def forward(ctx, q, kv, phantom, resid, graph: CrystalGraph, qpl: Optional[Planes], S: int):
+    def forward(ctx, q, kv, phantom, resid, graph: CrystalGraph, qpl: Optional[Planes], S: int, drop_p: float = 0.0, seed: int = 0):
         N, H = kv.shape
         B = graph.B
         T = q.shape[-2]
@@ -1354,7 +1354,7 @@ class _CrossAttentionTC(torch.autograd.Function):
         lse = torch.empty(S * T, dtype=torch.float32, device=dev)
         scale = float(H) ** -0.5
         L.check(lib.dost_xattn_softmax_fwd(L.p(scores), L.p(graph.ptr), L.p(graph.nmax), S * T, B, T, npad, scale, L.p(pp.hi),
-                                           L.p(pp.lo), pp.ld, L.p(lse), L.stream()), "xattn_softmax_fwd")
+                                           L.p(pp.lo), pp.ld, L.p(lse), drop_p, seed, L.stream()), "xattn_softmax_fwd")
         out = torch.empty(S, T, H, dtype=torch.float32, device=dev)
         r2 = resid.view(-1, H)
         gemm_planes(M=T, N=H, K=npad, a=[pp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=out.view(S * T, H), residual=r2,
@@ -1363,6 +1363,7 @@ class _CrossAttentionTC(torch.autograd.Function):
         ctx.save_for_backward(kv, phantom, scores, lse, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
         ctx.graph, ctx.prec, ctx.npad = graph, _PRECISION, npad
         ctx.bcast_q, ctx.bcast_r, ctx.T, ctx.S = bcast_q, resid.dim() == 2, T, S
+        ctx.drop_p, ctx.seed = drop_p, seed
         return out
 
     @staticmethod
@@ -1386,7 +1387,8 @@ class _CrossAttentionTC(torch.autograd.Function):
                         a_bstride=T * dop.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
             dsp = empty_planes(S * T, npad, dev, _with_lo())
             L.check(lib.dost_xattn_softmax_bwd(L.p(scores), L.p(lse), L.p(dP), L.p(g.ptr), L.p(g.nmax), S * T, B, T, npad,
-                                               float(H) ** -0.5, L.p(dsp.hi), L.p(dsp.lo), dsp.ld, L.stream()), "xattn_softmax_bwd")
+                                               float(H) ** -0.5, L.p(dsp.hi), L.p(dsp.lo), dsp.ld, ctx.drop_p, ctx.seed,
+                                               L.stream()), "xattn_softmax_bwd")
             # dQ = dS k
             dq = torch.empty(S, T, H, dtype=torch.float32, device=dev)
             gemm_planes(M=T, N=H, K=npad, a=[dsp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=dq.view(S * T, H), batch=S,
@@ -1408,7 +1410,7 @@ class _CrossAttentionTC(torch.autograd.Function):
             dph = colsum(dbrows)
             d_q = colsum(dq.view(S, T * H)).view(T, H) if ctx.bcast_q else dq
             d_resid = colsum(d_out.view(S, T * H)).view(T, H) if ctx.bcast_r else d_out
-        return d_q, dkv, dph, d_resid, None, None, None
+        return d_q, dkv, dph, d_resid, None, None, None, None, None
 
 
 def _rows(pl: Planes, r0: int, r1: int) -> Planes:
@@ -1418,10 +1420,10 @@ def _rows(pl: Planes, r0: int, r1: int) -> Planes:
 
 def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float = 0.0, seed: int = 0):
     H = kv.shape[1]
-    if (tc_active(kv) and H % 128 == 0 and drop_p == 0.0 and S % graph.B == 0 and graph.nmax_host is not None
+    if (tc_active(kv) and H % 128 == 0 and S % graph.B == 0 and graph.nmax_host is not None
             and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")
             and (q.dim() == 3 or S == graph.B)):
-        return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q), S)
+        return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q), S, drop_p, seed)
     return _CrossAttention.apply(q, kv, phantom, resid, graph, S, drop_p, seed)
 
 

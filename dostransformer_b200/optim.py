@@ -97,6 +97,32 @@ class AdamW:
             # version counters, e.g. the bf16 operand planes of the weights in ops.weight_planes) that they changed
             torch.autograd.graph.increment_version(touched)
 
+    @torch.no_grad()
+    def step_subset(self, params: List[torch.nn.Parameter], grads: List[torch.Tensor]) -> None:
+        """AdamW update of ``params`` with explicitly given (contiguous fp32) gradient tensors, on the CURRENT stream.
+        Used by dp.GradReducer.finish(optimizer=...): each bucket is updated straight from its all-reduced flat buffer as
+        soon as its reduction completes, so the update of bucket i overlaps the reduction of bucket i+1 and the
+        write-back copy into ``p.grad`` disappears (AdamW fused with the all-reduce epilogue)."""
+        group_of = {id(p): g for g in self.param_groups for p in g["params"]}
+        by_key = {}
+        for p, gr in zip(params, grads):
+            if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and gr.is_contiguous()):
+                raise RuntimeError("dostransformer_b200.optim.AdamW handles contiguous fp32 CUDA parameters only")
+            st = self._state_of(p)
+            st["step"] += 1
+            by_key.setdefault((id(group_of[id(p)]), st["step"]), []).append((p, gr))
+        for (gid, step), items in by_key.items():
+            grp = group_of[id(items[0][0])]
+            n = len(items)
+            arr = lambda xs: (C.c_void_p * n)(*xs)
+            L.check(L.lib().dost_adamw_step(
+                n, arr([p.data_ptr() for p, _ in items]), arr([g.data_ptr() for _, g in items]),
+                arr([self.state[p]["exp_avg"].data_ptr() for p, _ in items]),
+                arr([self.state[p]["exp_avg_sq"].data_ptr() for p, _ in items]),
+                (C.c_longlong * n)(*[p.numel() for p, _ in items]), float(grp["lr"]), float(grp["betas"][0]),
+                float(grp["betas"][1]), float(grp["eps"]), float(grp["weight_decay"]), step, L.stream()), "adamw_step")
+        torch.autograd.graph.increment_version(list(params))
+
     def state_dict(self):
         plist = self.params
         idx = {p: i for i, p in enumerate(plist)}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 9
+#define DOST_ABI_VERSION 10
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -282,11 +282,15 @@ int dost_xattn_kv_ext_build(const float* y, const float* beta, const int32_t* ba
                             int H, void* hi, void* lo, long long ldp, dost_stream_t stream);
 int dost_xattn_kv_ext_split(const float* dext, const int32_t* batch, const int32_t* ptr, long long N, int B, int H, float* dkv,
                             float* dbeta_rows, dost_stream_t stream);
+/* drop_p > 0: attention dropout (multihead_attention.py:71) with the counter-based mask of dost_xattn_fwd (index =
+ * row * Nmax + key slot; the Nmax - n_b phantom copies occupy the slots n_b .. Nmax-1 and survive individually): the planes
+ * hold mask / (1 - p) * P, the phantom column (surviving copies) / (1 - p) * P_phantom; the backward regenerates the mask. */
 int dost_xattn_softmax_fwd(const float* scores, const int32_t* ptr, const int32_t* nmax, long long rows, int B, int T, int npad,
-                           double scale, void* hi, void* lo, long long ldp, float* lse, dost_stream_t stream);
+                           double scale, void* hi, void* lo, long long ldp, float* lse, double drop_p, unsigned long long seed,
+                           dost_stream_t stream);
 int dost_xattn_softmax_bwd(const float* scores, const float* lse, const float* dP, const int32_t* ptr, const int32_t* nmax,
                            long long rows, int B, int T, int npad, double scale, void* hi, void* lo, long long ldp,
-                           dost_stream_t stream);
+                           double drop_p, unsigned long long seed, dost_stream_t stream);
 
 /* Row softmax for the dense T x T self attention (layers/multihead_attention.py:68-70): p = softmax_fp32(s*scale);
  * pd = dropout(p); rows are ld elements apart (ld >= cols).  Backward: ds = scale * p * (dp - sum(dp*p)) with dp = mask/(1-p) * dpd. */

@@ -48,10 +48,22 @@ def main():
     step(mine)
     torch.cuda.synchronize()
     graphed = {k: p.grad.detach().cpu().clone() for k, p in dp.live_named_parameters(model)}
+    # AdamW fused into the all-reduce epilogue: every bucket is updated straight from its reduced flat buffer
+    from dostransformer_b200.optim import AdamW
+    del step
+    opt = AdamW(model.parameters(), lr=1e-3, weight_decay=1e-2)
+    reducer2 = dp.GradReducer(dp.live_named_parameters(model), bucket_bytes=256 << 10)
+    model.zero_grad(set_to_none=True)
+    dg, x, ds = model(mine)
+    (ops.dos_loss(dg, ds, mine.y_ft, mode="edos", beta=1.0) * weights[rank]).backward()
+    reducer2.finish(optimizer=opt)
+    torch.cuda.synchronize()
+    stepped = {k: p.detach().cpu().clone() for k, p in dp.live_named_parameters(model)}
+    reducer2.remove()
     lsum = torch.tensor([float(loss)], device=dev, dtype=torch.float64)
     dist.all_reduce(lsum)
     if rank == 0:
-        torch.save({"runs": runs, "graphed": graphed, "nbuckets": len(reducer.buckets), "loss": float(lsum.item()),
+        torch.save({"runs": runs, "graphed": graphed, "stepped": stepped, "nbuckets": len(reducer.buckets), "loss": float(lsum.item()),
                     "bins": bins, "nmax": nmax}, os.path.join(out_dir, "rank0.pt"))
     dist.barrier()
     dist.destroy_process_group()

@@ -75,8 +75,15 @@ def test_graph_replay_sees_optimizer_updates():
     assert torch.equal(l2, want2)
 
 
-def test_bucket_padding_leaves_the_real_crystals_unchanged():
-    m = _model(h=128)
+@pytest.mark.parametrize("prec,tol", [("fp32", 1e-4), ("bf16x3", 5e-3)])
+def test_bucket_padding_leaves_the_real_crystals_unchanged(prec, tol):
+    """Dummy crystals contribute exact zeros to every gradient; what differs from the unpadded step is the summation
+    grouping (split-K chunks move with the row count).  fp32 path: fp32 rounding only (1e-4 on the cancellation-prone
+    first-stack tensors).  bf16x3: the tensor-core accumulation order moves too and the same tensors amplify it to the
+    level of that path's stated gradient floor (tests/test_gpu_model.py GRAD_FLOOR: rel-L2 2e-3 vs fp64; two bf16x3
+    evaluations with different groupings may differ by twice that).  The semantic no-op itself is pinned on the CPU oracle
+    (tests/test_host.py::test_bucket_padding_is_a_semantic_no_op_for_the_real_crystals)."""
+    m = _model(h=128, prec=prec)
     g = make_edos_batch(7, seed=41, mean_atoms=9.0)
     p = pad_edos_batch(g, node_bucket=64, dummies=3)
     assert p.n_valid == 7 and p.system.numel() >= 10 and p.x.shape[0] % 64 == 0      # (the dummy count doubles until each fits)
@@ -86,21 +93,20 @@ def test_bucket_padding_leaves_the_real_crystals_unchanged():
     step = GraphedStep(m, "edos")
     for _ in range(2):
         got_loss = step(p.clone().to(DEV))
-    assert abs(got_loss.item() - want_loss.item()) <= 1e-6 * abs(want_loss.item())
-    # the dummy crystals contribute exact zeros; what differs is the summation grouping (split-K chunks move with the row
-    # count), which the cancellation-prone first-stack gradients amplify (embeddings.weight, transformer.layers.*.fc1;
-    # the reference's own fp32-vs-fp64 error there is 1e-3): graded at the stated bf16x3 gradient floor
-    for k, pr in m.named_parameters():
-        if k in want:
-            err = ((pr.grad.double() - want[k].double()).norm() / want[k].double().norm().clamp_min(1e-30)).item()
-            assert err < 2e-3, (k, err)      # GRAD_FLOOR["bf16x3"] of tests/test_gpu_model.py
+    assert abs(got_loss.item() - want_loss.item()) <= 2e-6 * abs(want_loss.item())
+    errs = {k: ((pr.grad.double() - want[k].double()).norm() / want[k].double().norm().clamp_min(1e-30)).item()
+            for k, pr in m.named_parameters() if k in want}
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, bad
     # model outputs of the real crystals are the unpadded ones
     m.eval()
     with torch.no_grad():
         dg_p, x_p, ds_p = m(p.clone().to(DEV))
         dg, x, ds = m(g.clone().to(DEV))
-    assert (dg_p[:7] - dg).abs().max().item() <= 1e-5 * dg.abs().max().item()
-    assert (x_p[:x.shape[0]] - x).abs().max().item() <= 1e-5 * x.abs().max().item()
+    # (1e-4 = the stated output tolerance: with more rows some small Linears move from the fp32 FMA kernel to the
+    # bf16x3 tensor-core kernel, ops.planes_gemm_ok)
+    assert (dg_p[:7] - dg).abs().max().item() <= 1e-4 * dg.abs().max().item()
+    assert (x_p[:x.shape[0]] - x).abs().max().item() <= 1e-4 * x.abs().max().item()
 
 
 def test_graphed_inference_matches_eager():

@@ -928,11 +928,20 @@ def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, 
             wide = torch.zeros(M, 2 * N + 8, device=DEV)
             ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, out=wide[:, N:2 * N])
             outs["wide"] = wide
+            # (5) batched problems (the attention contractions): 3-D store map, a box never spans two problems
+            nb_, Mb, Nb = 5, min(M, 201), min(N, 256)
+            qa = ops.split_planes(a[:Mb].repeat(nb_, 1) * torch.arange(1, nb_ + 1, device=DEV).repeat_interleave(Mb)[:, None])
+            kb = ops.split_planes(torch.randn(nb_ * Nb, K, generator=torch.Generator(device=DEV).manual_seed(3), device=DEV))
+            ob = torch.full((nb_ * Mb, Nb), float("nan"), device=DEV)
+            rsd = res[:Mb, :Nb].repeat(nb_, 1).contiguous()
+            ops.gemm_planes(M=Mb, N=Nb, K=K, a=[qa], a_mode=L.KC, b=kb, b_mode=L.KC, b_rows=Nb, out=ob, residual=rsd, batch=nb_,
+                            a_bstride=Mb * qa.ld, b_bstride=Nb * kb.ld, c_bstride=Mb * Nb, res_bstride=Mb * Nb)
+            outs["batched"] = ob
         torch.cuda.synchronize()
         return outs
 
     reg, tma = run(False), run(True)
-    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide"):
+    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide", "batched"):
         if reg[k] is None:
             continue
         assert not torch.isnan(tma[k].float()).any(), k
@@ -942,3 +951,34 @@ def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, 
     want = (a.double() @ (w.double().T if bm == L.KC else w.double())) * torch.where(saved > 0, 1.0, 0.0).double()
     if prec == "bf16x3":
         assert (tma["colsum"].double() - want.sum(0)).abs().max() / want.sum(0).abs().max() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reps", [1, 2])
+def test_cross_attention_dropout_on_tensor_cores_equals_fma_kernels(reps):
+    """Attention dropout (multihead_attention.py:71) on the tensor-core cross-attention: the softmax kernel applies the
+    counter-based mask (index = row * Nmax + key slot; the phantom copies survive individually) while it writes the
+    probability planes, the backward regenerates it.  Same seed => same mask as the fused FMA kernels (attention_v2.cu):
+    outputs and all gradients must agree (bf16x3 vs fp32 arithmetic: 1e-4).  reps = 2: the global and the system branch
+    batched as 2 B sequences (sequence s attends to crystal s % B)."""
+    from dostransformer_b200.synthetic import make_edos_batch
+    g = make_edos_batch(5, seed=37, mean_atoms=9.0, max_atoms=40)
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV), nmax_hint=g.max_num_nodes)
+    B, T, H = gr.B, 70, 128
+    S = reps * B
+    kv0, ph0, q0 = _rand(gr.N, H, seed=1), _rand(H, seed=2), _rand(S, T, H, seed=3)
+    wgt = _rand(S, T, H, seed=4)
+    res = {}
+    for name, prec in (("tc", "bf16x3"), ("fma", "fp32")):
+        kv, ph, q = _leaf(kv0.clone()), _leaf(ph0.clone()), _leaf(q0.clone())
+        with ops.precision(prec):
+            out = ops.cross_attention(q, kv, ph, q, gr, S, 0.25, 4242)
+            assert type(out.grad_fn).__name__.startswith("_CrossAttentionTC" if name == "tc" else "_CrossAttentionBackward")
+            (out * wgt).sum().backward()
+        res[name] = (out.detach(), kv.grad, ph.grad, q.grad)
+    for nm, a_, b_ in zip(["out", "dkv", "dphantom", "dq"], res["tc"], res["fma"]):
+        assert relerr(a_, b_) < 1e-4, (nm, relerr(a_, b_))
+    # and dropout really happened
+    with ops.precision("bf16x3"):
+        base = ops.cross_attention(q0, kv0, ph0, q0, gr, S, 0.0, 0)
+    assert relerr(res["tc"][0], base) > 1e-2
