@@ -348,20 +348,39 @@ def _to_device(g, dev):
 
 
 class Runner:
-    """One configuration's step function: eager (`model(batch)` + ops.dos_loss + backward + GradReducer) or whole-step
-    CUDA-graph replay (graphed.GraphedStep + flat all-reduce)."""
+    """One configuration's step function: whole-step CUDA-graph replay (graphed.GraphedStep + flat all-reduce) or the eager
+    step (`model(batch)` + ops.dos_loss + backward + bucketed GradReducer).  A capture that fails (first call of a new
+    batch signature) falls back to the eager step for the rest of the run and says so in `mode`."""
 
     def __init__(self, model, mode, world, weight, use_graph, reducer=None):
-        from dostransformer_b200 import ops
+        from dostransformer_b200 import dp, ops
         from dostransformer_b200.graphed import GraphedStep
-        self.model, self.mode, self.world, self.weight, self.ops = model, mode, world, weight, ops
+        self.model, self.mode, self.world, self.weight, self.ops, self.dp = model, mode, world, weight, ops, dp
         self.reducer = reducer
+        self.own_reducer = False
         self.graph = GraphedStep(model, mode, loss_weight=weight, world=world) if use_graph else None
         self.tkey = "y_ft" if mode == "edos" else "phdos"
+        self.fallback = None
+
+    def describe(self):
+        if self.graph is not None:
+            return "whole-step CUDA-graph replay (graphed.GraphedStep)" + (", flat NCCL all-reduce after the replay" if self.world > 1 else "")
+        base = "eager step" + (", bucketed all-reduce overlapped with backward" if self.world > 1 else "")
+        return base + (f" (graph capture failed: {self.fallback})" if self.fallback else "")
 
     def __call__(self, g):
         if self.graph is not None:
-            return self.graph(g)
+            try:
+                return self.graph(g)
+            except Exception as ex:  # noqa: BLE001  (a failed capture must not take the measurement down)
+                if self.graph.replays > 0:
+                    raise
+                self.fallback = repr(ex)[:200]
+                self.graph = None
+                torch.cuda.synchronize()
+        if self.reducer is None and self.world > 1:
+            self.reducer = self.dp.GradReducer(self.dp.live_named_parameters(self.model))
+            self.own_reducer = True
         model = self.model
         model.zero_grad(set_to_none=True)
         dg, _, ds = model(g)
@@ -372,6 +391,12 @@ class Runner:
         if self.reducer is not None:
             self.reducer.finish()
         return loss.detach()
+
+    def close(self):
+        if self.reducer is not None and self.own_reducer:
+            self.reducer.remove()
+        self.reducer = None
+        self.graph = None
 
     def launches(self, L, l0):
         return (self.graph.launches if self.graph is not None else 0) + (L.launch_count() - l0)
@@ -454,8 +479,7 @@ def strong_scaling_leg(model, rank, world, dev, steps, warmup, barrier, st, glob
         nmaxes.append(nmax)
     old_nmax = model.max_num_nodes
     model.max_num_nodes = max(nmaxes)        # the sharder's global padding length (one value for the 3 rotating batches)
-    reducer = dp.GradReducer(dp.live_named_parameters(model)) if (world > 1 and not use_graph) else None
-    run = Runner(model, "edos", world, weights[rank] if world > 1 else 1.0, use_graph, reducer)
+    run = Runner(model, "edos", world, weights[rank] if world > 1 else 1.0, use_graph)
     resident = [p.clone().to(dev) for p in parts]
     l0 = L.launch_count()
     sec, each = timed_steps(run, resident, steps, max(warmup, NB), barrier, st)
@@ -463,8 +487,8 @@ def strong_scaling_leg(model, rank, world, dev, steps, warmup, barrier, st, glob
     sec = max_over_ranks(sec, world, dev)
     e2e_sec, _ = e2e_steps(run, parts, dev, steps, warmup, barrier)
     e2e_sec = max_over_ranks(e2e_sec, world, dev)
-    if reducer is not None:
-        reducer.remove()
+    mode_desc = run.describe()
+    run.close()
     model.max_num_nodes = old_nmax
     b_local = int(parts[0].system.numel())
     return {"metric": METRIC, "value": global_batch * steps / sec, "unit": UNIT, "scaling": "strong", "n_gpus": world,
@@ -475,9 +499,7 @@ def strong_scaling_leg(model, rank, world, dev, steps, warmup, barrier, st, glob
             "config": {"workload": f"{MODEL_DESC} T={T}, training step, GLOBAL batch {global_batch} crystals with ragged atom counts, "
                                    f"data-parallel {world}xB200 through the LPT sharder (BASELINE configs[2])",
                        "global_batch": global_batch, "crystals_per_gpu": b_local, "parallelism": f"dp{world}",
-                       "mode": ("whole-step CUDA-graph replay (graphed.GraphedStep), flat NCCL all-reduce after the replay"
-                                if use_graph else "eager step, bucketed overlapped all-reduce"),
-                       "nmax": max(nmaxes)}}
+                       "mode": mode_desc, "nmax": max(nmaxes)}}
 
 
 def weak_leg(model, workload, mode, B, rank, world, dev, steps, warmup, barrier, st, use_graph, L, label):
@@ -496,15 +518,14 @@ def weak_leg(model, workload, mode, B, rank, world, dev, steps, warmup, barrier,
             b["max_num_nodes"] = int(torch.bincount(b.batch).max())
     old_nmax = model.max_num_nodes
     model.max_num_nodes = nmax
-    reducer = dp.GradReducer(dp.live_named_parameters(model)) if (world > 1 and not use_graph) else None
-    run = Runner(model, mode, world, 1.0 / world, use_graph, reducer)
+    run = Runner(model, mode, world, 1.0 / world, use_graph)
     resident = [b.clone().to(dev) for b in host]
     l0 = L.launch_count()
     sec, each = timed_steps(run, resident, steps, max(warmup, NB), barrier, st)
     launches = run.launches(L, l0)
     sec = max_over_ranks(sec, world, dev)
-    if reducer is not None:
-        reducer.remove()
+    mode_desc = run.describe()
+    run.close()
     model.max_num_nodes = old_nmax
     n_nodes = sum(b.batch.numel() for b in host) / NB
     n_edges = sum(b.edge_index.shape[1] for b in host) / NB
@@ -513,7 +534,7 @@ def weak_leg(model, workload, mode, B, rank, world, dev, steps, warmup, barrier,
             "gpu_launches_per_step": launches / max(1, steps + max(warmup, NB)),
             "config": {"workload": label, "crystals_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
                        "mean_nodes_per_batch": n_nodes, "mean_edges_per_batch": n_edges, "nmax": nmax,
-                       "mode": "whole-step CUDA-graph replay" if use_graph else "eager"}}
+                       "mode": mode_desc}}
 
 
 def sweep_leg(model, rank, world, dev, n_eval, store_size, batch_size, barrier):
@@ -649,7 +670,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
 
     B = args.batch
     strong = args.scaling == "strong"
-    use_graph = {"on": True, "off": False, "auto": (strong or B < 256)}[args.graph]
+    use_graph = {"on": True, "off": False, "auto": True}[args.graph]
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -684,13 +705,11 @@ def run_product(args, rank: int, world: int, local_rank: int):
     if args.nmax > 0:
         nmax = max(nmax, args.nmax)
     model.max_num_nodes = nmax            # global padding length: the only cross-rank coupling besides the grads
-    reducer = GradReducer(live_named_parameters(model)) if (world > 1 and not use_graph
-                                                           and not os.environ.get("DOST_BENCH_NO_REDUCER")) else None
-    step = Runner(model, "edos", world, 1.0 / world, use_graph, reducer)
+    step = Runner(model, "edos", world, 1.0 / world, use_graph)
     resident = [b.clone().to(dev) for b in host]
 
     # ---------------------------------------------------------------- device-resident timing
-    for i in range(args.warmup):
+    for i in range(max(args.warmup, NB)):      # (every batch signature once: graph capture / allocator warm-up)
         step(resident[i % NB])
     barrier()
     if rank == 0:
@@ -721,18 +740,20 @@ def run_product(args, rank: int, world: int, local_rank: int):
         "config": {"workload": wl_desc, "crystals_per_gpu": B,
                    "global_batch": B * world, "parallelism": f"dp{world}", "mean_nodes_per_batch": n_nodes,
                    "mean_edges_per_batch": n_edges, "nmax": nmax, "precision": PREC_DESC[args.precision],
-                   "mode": "whole-step CUDA-graph replay" if use_graph else "eager",
+                   "mode": step.describe(),
                    "l2_policy": "3 distinct batches rotated; per-step activations (>1 GB) exceed the 126 MB L2"},
         "clocks": clocks, "gpu_launches": int(launches), "ms_each_step_device": dev_each,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_sec / args.steps * 1e3, "ms_each_step": [round(x, 2) for x in per_step],
-                "api": "DOSTransformer(batch) + ops.dos_loss + loss.backward(), batch copied from pinned host memory, "
-                       "loss.item() every step; gc.freeze() after warm-up, cyclic GC off inside the timed loop"},
+                "api": ("graphed.GraphedStep(model)(batch) [forward + ops.dos_loss + backward as one CUDA-graph replay]" if
+                        step.graph is not None else "DOSTransformer(batch) + ops.dos_loss + loss.backward()") +
+                       ", batch copied from pinned host memory, loss.item() every step; gc.freeze() after warm-up, cyclic GC "
+                       "off inside the timed loop"},
     }
     fl = 3.0 * B * flops_per_crystal_fwd(n_nodes / B, n_edges / B, nmax)
     line["model_tflops"] = fl * args.steps / sec / 1e12
-    if reducer is not None:
-        reducer.remove()
+    headline_graph = step.graph is not None
+    step.close()
 
     extras = not args.no_extras and args.workload == "edos" and B == 512
 
@@ -802,6 +823,10 @@ def run_product(args, rank: int, world: int, local_rank: int):
         from dostransformer_b200.optim import AdamW
         opt = AdamW(model.parameters(), lr=1e-4, weight_decay=1e-2)
         eager = Runner(model, "edos", 1, 1.0, False)
+        esec, _ = timed_steps(eager, resident, args.steps, 3, barrier, st)
+        line["eager_mode"] = {"value": B * args.steps / esec, "unit": UNIT, "ms_per_step": esec / args.steps * 1e3,
+                              "what": "the same step issued kernel by kernel from Python (model(batch) + ops.dos_loss + "
+                                      "loss.backward()), device-resident batches; bitwise the same results as the graph replay"}
         eager(resident[0])
         opt.step()
         torch.cuda.synchronize()
@@ -949,7 +974,7 @@ def main():
                     help="weak = the headline (per-GPU batch fixed); strong = BASELINE configs[2] as written (global batch "
                          "through the LPT sharder)")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="whole-step CUDA-graph replay (auto: strong scaling and per-GPU batches below 256)")
+                    help="whole-step CUDA-graph replay (auto = on, falling back to the eager step if a capture fails)")
     ap.add_argument("--cpu-sample", type=int, default=64, help="crystals per step of the CPU baseline sample")
     ap.add_argument("--cpu-steps", type=int, default=20, help="timed CPU baseline steps (bounded sample, ~10-20 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

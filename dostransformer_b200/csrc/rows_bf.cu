@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------- LayerNorm backward
-// dx = LN'(dy) (+ dres); also dgamma, dbeta, dslope and (optionally) the column sums of dx (the bias gradient of the
+// dx = LN'(dy) (+ dres); also dgamma, dbeta, dslope and (optionally) the column sums of the stored dx (the bias gradient of the
 // Linear that feeds the LayerNorm).  dx is written as fp32 and/or as planes.
 // ws layout: [nblocks][3 * W + 1] = (dgamma, dbeta, dxsum, dslope) partials.
 template <int NV>
@@ -181,11 +181,11 @@ __global__ void __launch_bounds__(kWarps * 32) ln_bwd_kernel(const float* __rest
       o.y = rstd * (g[i].y - s1 - xh[i].y * s2);
       o.z = rstd * (g[i].z - s1 - xh[i].z * s2);
       o.w = rstd * (g[i].w - s1 - xh[i].w * s2);
-      dxs[i].x += o.x; dxs[i].y += o.y; dxs[i].z += o.z; dxs[i].w += o.w;
       if (dres) {
         const float4 q = __ldg(reinterpret_cast<const float4*>(dres + r * ld_dres) + lane + 32 * i);
         o.x += q.x; o.y += q.y; o.z += q.z; o.w += q.w;
       }
+      dxs[i].x += o.x; dxs[i].y += o.y; dxs[i].z += o.z; dxs[i].w += o.w;      // column sums of the STORED value (incl. dres)
       if (dx) reinterpret_cast<float4*>(dx + r * (long long)W)[lane + 32 * i] = o;
       if (dx_hi) {
         uint2 h, l;

@@ -124,13 +124,17 @@ def message_passing(processors, x, e, graph: ops.CrystalGraph, mean: bool):
     return x
 
 
-def _ffn(layer, y2d):
+def _ffn(layer, y):
+    """y [S, T, H] -> y + fc2(relu(fc1(LN1(y)))), same shape (layers/transformer.py:141-148)."""
     ln1 = layer.layer_norms[1]
-    if ops.tc_active(y2d) and ops.planes_ok(y2d.shape[1]) and y2d.shape[0] >= 128 and not L.switch("DOST_NO_FFNBLOCK"):
-        return ops.ffn_block(y2d, ln1.weight, ln1.bias, layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias)
+    H = y.shape[-1]
+    rows = y.numel() // H
+    if ops.tc_active(y) and ops.planes_ok(H) and rows >= 128 and not L.switch("DOST_NO_FFNBLOCK"):
+        return ops.ffn_block(y, ln1.weight, ln1.bias, layer.fc1.weight, layer.fc1.bias, layer.fc2.weight, layer.fc2.bias)
+    y2d = y.reshape(rows, H)
     h = ops.layer_norm(y2d, ln1.weight, ln1.bias)
     h = ops.linear([(h, None)], layer.fc1.weight, layer.fc1.bias, act=L.ACT_RELU)
-    return ops.linear([(h, None)], layer.fc2.weight, layer.fc2.bias, residual=y2d)
+    return ops.linear([(h, None)], layer.fc2.weight, layer.fc2.bias, residual=y2d).view(y.shape)
 
 
 class _Seeds:
@@ -152,7 +156,7 @@ def cross_stack(enc: EnergyEncoderParams, q, x_nodes, graph: ops.CrystalGraph, S
         kv = ops.layer_norm(x_nodes, ln0.weight, ln0.bias)
         q_ln, q_res = ops.layer_norm(q, ln0.weight, ln0.bias, want_planes=q.dim() == 3, with_residual=True)
         y = ops.cross_attention(q_ln, kv, ln0.bias, q_res, graph, S, seeds.p, seeds.next())
-        q = _ffn(layer, y.view(S * T, H)).view(S, T, H)
+        q = _ffn(layer, y)
     return ops.layer_norm(q, enc.layer_norm.weight, enc.layer_norm.bias)
 
 
@@ -169,7 +173,7 @@ def self_stack(enc: EnergyEncoderParams, x0, seeds: _Seeds):
             k = ops.layer_norm(x0, ln0.weight, ln0.bias, want_planes=True)
             q, x_res = ops.layer_norm(x, ln0.weight, ln0.bias, want_planes=True, with_residual=True)
         y = ops.self_attention(q, k, x_res, seeds.p, seeds.next())
-        x = _ffn(layer, y.view(S * T, H)).view(S, T, H)
+        x = _ffn(layer, y)
     return ops.layer_norm(x, enc.layer_norm.weight, enc.layer_norm.bias)
 
 

@@ -575,8 +575,12 @@ class _FFNBlock(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, y, ln_w, ln_b, w1, b1, w2, b2):
-        M, H = y.shape
+    def forward(ctx, y_nd, ln_w, ln_b, w1, b1, w2, b2):
+        H = y_nd.shape[-1]
+        y = y_nd.reshape(-1, H)
+        if y.stride(-1) != 1 or (y.shape[0] > 1 and y.stride(0) != H):
+            y = y.contiguous()
+        M = y.shape[0]
         F = w1.shape[0]
         dev = y.device
         _, h0p, stats = ln_fwd_planes(y, ln_w, ln_b)
@@ -587,10 +591,11 @@ class _FFNBlock(torch.autograd.Function):
         gemm_planes(M=M, N=H, K=F, a=[h1p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=y, out=out)
         ctx.save_for_backward(y, stats, ln_w, ln_b, w1, w2, *_planes_save(h0p), *_planes_save(h1p))
         ctx.prec = _PRECISION
-        return out
+        ctx.shape = y_nd.shape
+        return out.view(y_nd.shape)
 
     @staticmethod
-    def backward(ctx, d_out):
+    def backward(ctx, d_out_nd):
         y, stats, ln_w, ln_b, w1, w2, h0h, h0l, h1h, h1l = ctx.saved_tensors
         M, H = y.shape
         F = w1.shape[0]
@@ -598,8 +603,16 @@ class _FFNBlock(torch.autograd.Function):
         with precision_value(ctx.prec):
             h0p, h1p = _planes_load(h0h, h0l, M, H), _planes_load(h1h, h1l, M, F)
             w1p, w2p = weight_planes(w1), weight_planes(w2)
-            d_out = d_out.contiguous()
-            dop, db2 = split_planes_colsum(d_out)
+            # the LayerNorm backward that produced this gradient may already have written its operand planes and column
+            # sums in the same pass (_LayerNorm.backward, `emit_grad_planes`): one pass over d_out saved
+            dop = getattr(d_out_nd, "_dost_planes", None)
+            db2 = getattr(d_out_nd, "_dost_colsum", None)
+            d_out = d_out_nd.reshape(M, H)
+            if d_out.stride(-1) != 1 or (M > 1 and d_out.stride(0) != H):
+                d_out, dop = d_out.contiguous(), None
+            if dop is None or db2 is None or dop.rows != M or dop.cols != H or (dop.lo is not None) != _with_lo() or \
+                    getattr(d_out_nd, "_dost_planes_version", -1) != d_out_nd._version:
+                dop, db2 = split_planes_colsum(d_out)
             dw2 = torch.empty(H, F, dtype=torch.float32, device=dev)
             gemm_planes(M=H, N=F, K=M, a=[dop], a_mode=L.MC, b=h1p, b_mode=L.MC, out=dw2, split_k=_split_for(H, F, M))
             # d(relu input) = (d_out W2) * relu'(h1): relu' from the sign of the saved hi plane, result as planes only
@@ -612,11 +625,15 @@ class _FFNBlock(torch.autograd.Function):
             dh0 = torch.empty(M, H, dtype=torch.float32, device=dev)
             gemm_planes(M=M, N=H, K=F, a=[dv1p], a_mode=L.KC, b=w1p, b_mode=L.MC, out=dh0)
             dy, _, dg, db, _, _ = ln_bwd_planes(dh0, y, stats, ln_w, ln_b, dres=d_out)
-        return dy, dg, db, dw1, db1, dw2, db2
+        return dy.view(ctx.shape), dg, db, dw1, db1, dw2, db2
 
 
-def ffn_block(y2d, ln_w, ln_b, w1, b1, w2, b2):
-    return _FFNBlock.apply(y2d, ln_w, ln_b, w1, b1, w2, b2)
+def ffn_block(y, ln_w, ln_b, w1, b1, w2, b2):
+    """y [..., H] -> y + fc2(relu(fc1(LN(y)))) in y's shape.  The result is tagged so that a LayerNorm that consumes it
+    (the next layer's LN0 / the stack's final LayerNorm) emits its input gradient as operand planes + column sums too."""
+    out = _FFNBlock.apply(y, ln_w, ln_b, w1, b1, w2, b2)
+    out._dost_ffn_out = True
+    return out
 
 
 def cols_view(pl: Planes, a: int, b: int) -> Planes:
@@ -820,6 +837,9 @@ class _Linear(torch.autograd.Function):
             segs = [(tensors[ti], spec.maps[si]) for si, ti in enumerate(spec.tensor_of_seg)]
             gemm_raw(M=M, N=N, K=K, a=segs, a_mode=L.KC, b=weight, b_mode=L.KC, out=out, bias=bias, act=spec.act,
                      act_slope=spec.act_slope, prelu_slope=slope, out_pre=pre, residual=residual)
+        # (the output buffer is a view whose base is the stacked tensor that _Stack2 returns with THIS node behind it:
+        # keeping it on the ctx would close a reference cycle that only the cyclic GC could free, a [2 B T, H] tensor each)
+        spec.out_buf = None
         ctx.spec = spec
         ctx.prec = _PRECISION
         ctx.n_tensors = len(tensors)
@@ -1177,6 +1197,9 @@ class _LayerNorm(torch.autograd.Function):
         ctx.n_planes = 0
         ctx.with_residual = with_residual
         ctx.shape = x.shape
+        # x is the output of an FFN block whose backward wants this node's dx as GEMM operand planes + its column sums
+        ctx.emit_grad_planes = bool(getattr(x, "_dost_ffn_out", False)) and _PRECISION != L.PREC_FMA
+        ctx.prec = _PRECISION
         outs = []
         if ctx.vec:       # 16-byte vectorised fp32 kernels (rows_bf.cu)
             y, pl, stats = ln_fwd_planes(x2, gamma, beta, slope, want_y=True, want_planes=want_planes)
@@ -1215,6 +1238,15 @@ class _LayerNorm(torch.autograd.Function):
             dy2 = dy2.contiguous()
         if ctx.vec and dy2.stride(0) % 4 == 0 and dy2.data_ptr() % 16 == 0 and \
                 (d_res is None or (d_res.stride(0) % 4 == 0 and d_res.data_ptr() % 16 == 0)):
+            if ctx.emit_grad_planes:
+                with precision_value(ctx.prec):
+                    dx, pl, dg, db, ds, xs = ln_bwd_planes(dy2, x2, stats, gamma, beta, slope, dres=d_res, want_planes=True,
+                                                           want_xsum=True)
+                out = dx.view(ctx.shape)
+                # read by _FFNBlock.backward when this very tensor object reaches it unmodified (single consumer; an
+                # in-place accumulation by autograd would bump the version counter)
+                out._dost_planes, out._dost_colsum, out._dost_planes_version = pl, xs, out._version
+                return out, dg, db, ds, None, None
             dx, _, dg, db, ds, _ = ln_bwd_planes(dy2, x2, stats, gamma, beta, slope, dres=d_res)
             return dx.view(ctx.shape), dg, db, ds, None, None
         dev, dtype = x2.device, x2.dtype

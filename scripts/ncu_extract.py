@@ -10,10 +10,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KEYS = ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active",
-        "sm__inst_executed_pipe_tensor", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput",
-        "lts__t_bytes.sum", "launch__registers_per_thread", "launch__grid_size", "smsp__cycles_active.avg",
-        "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_bank_conflicts", "smsp__warp_issue_stalled",
-        "sm__cycles_elapsed.max", "sm__pipe_tensor_subpipe", "tensor")
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg", "lts__throughput.avg",
+        "lts__t_bytes.sum", "launch__registers_per_thread", "launch__grid_size", "launch__cluster",
+        "sm__cycles_elapsed.max", "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime", "sm__mem_tensor_cycles_active.avg",
+        "l1tex__data_pipe_tc", "sm__inst_executed.avg.per_cycle_elapsed")
+SKIP = ("sm__ops_path", ".min", ".max.", ".sum.pct", "per_second")
 
 
 def raw(path):
@@ -41,7 +42,7 @@ def main():
         for rec in recs:
             lines.append(f"kernel: {rec.get('Kernel Name', '')[:120]}  grid {rec.get('Grid Size')} block {rec.get('Block Size')}")
             for k, v in rec.items():
-                if any(key in k for key in KEYS):
+                if any(key in k for key in KEYS) and not any(x in k for x in SKIP):
                     lines.append(f"  {k} [{units.get(k, '')}] = {v}")
             rd, wr = num(rec.get("dram__bytes_read.sum", "")), num(rec.get("dram__bytes_write.sum", ""))
             if rd is not None and wr is not None:
@@ -49,6 +50,11 @@ def main():
                 rd *= scale.get(units.get("dram__bytes_read.sum", "byte"), 1.0)
                 wr *= scale.get(units.get("dram__bytes_write.sum", "byte"), 1.0)
                 lines.append(f"  => DRAM traffic of this launch: {(rd + wr) / 1e6:.1f} MB (read {rd / 1e6:.1f}, write {wr / 1e6:.1f})")
+                act = num(rec.get("TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", ""))
+                el = num(rec.get("sm__cycles_elapsed.max", ""))
+                if act and el:
+                    lines.append(f"  => tensor pipe active {act / 4 / el * 100:.1f} % of the elapsed SM cycles (the realtime counter ticks once per "
+                                 f"sub-partition: hmma_cycles_active_realtime / 4 / sm__cycles_elapsed)")
                 out_traffic[name] = rd + wr
         with open(os.path.join(ROOT, "profiles", name + ".summary.txt"), "w") as f:
             f.write("\n".join(lines) + "\n")

