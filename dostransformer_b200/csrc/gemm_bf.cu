@@ -26,10 +26,8 @@ namespace dost {
 namespace bf {
 
 constexpr int BM = 128, BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (kEpiWarps + 2) * 32;  // 320
 constexpr int kMaxStages = 6;
-constexpr int kEpiBytes = kEpiWarps * 4096;     // one XOR-swizzled 32 x 32 fp32 staging tile per epilogue warp
+constexpr int kEpiBytes = 8 * 4096;             // staging: 8 epilogue warps x one 32 x 32 fp32 tile, or 16 warps x one 32 x 16 tile
 constexpr int kSmemBudget = 225 * 1024;         // stages + staging (+ 1 KB alignment slack <= 227 KB)
 
 struct Maps {
@@ -113,6 +111,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+template <int CW>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CW]) {
+  if constexpr (CW == 32) tmem_ld32(taddr, r);
+  else tmem_ld16(taddr, r);
 }
 // ---- cta_group::2 (CTA pair) helpers
 __device__ __forceinline__ uint32_t cluster_ctarank() {
