@@ -294,8 +294,11 @@ __device__ __forceinline__ TileInfo tile_info(const Params& p, int tile, int ran
   return t;
 }
 
-template <int NSPLIT, int BN, bool CTA2>
-__global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_constant__ Maps maps, const Params p) {
+// EW = number of epilogue warps: 8 (32-column chunks; both epilogue variants) or 16 (TMA-store epilogue only, 16-column
+// chunks: twice the warps per scheduler to hide the chunk's latency chain, <= 112 registers per thread).
+template <int NSPLIT, int BN, bool CTA2, int EW = 8>
+__global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_constant__ Maps maps, const Params p) {
+  constexpr int kEpiWarps = EW;
   constexpr bool SPLIT = NSPLIT == 3;
   constexpr int BNL = CTA2 ? BN / 2 : BN;          // B rows (output columns) this CTA stages per k-tile
   constexpr int A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2;
@@ -471,9 +474,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
     float pslope = 0.f;
     if (p.act == DOST_ACT_PRELU) pslope = __ldg(p.prelu_slope);
     else if (p.act == DOST_ACT_LEAKY) pslope = p.act_slope;
-    constexpr int CH = BN / 2;                            // accumulator columns handled by this warp
+    constexpr int NPART = EW / 4;                          // column parts of the accumulator (one per warp of a lane quarter)
+    constexpr int CH = BN / NPART;                         // accumulator columns handled by this warp
+    constexpr int CW = EW == 16 ? 16 : 32;                 // columns per chunk (one tcgen05.ld, one staging tile, one store)
+    constexpr int STG_BYTES = kEpiBytes / EW;              // this warp's staging tile: 32 rows x CW fp32, or hi + lo planes
     const int quad = warp & 3, half = warp >> 2;
-    const uint32_t stg = smem_u32(epi_smem) + warp * 4096;  // this warp's 32 x 32 fp32 staging tile (128-byte rows)
+    const uint32_t stg = smem_u32(epi_smem) + warp * STG_BYTES;
     const int rsub = lane >> 3, cj = lane & 7;             // after the transpose: rows rsub + 4 i, 16-byte column chunk cj
     const uint32_t acce_remote0 = CTA2 ? mapa_rank(acce0, 0) : 0u;   // the leader's accumulator-empty barriers
     // Feature switches and the hot pointers / strides live in registers for the whole kernel: read from the parameter
@@ -503,7 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
       // TMA-store epilogue: the side inputs of a chunk (residual, act' mask) do not depend on the accumulator.  They are
       // requested one chunk ahead - the first chunk's before this warp even waits for the MMAs of the tile - so their DRAM
       // latency (~1-2 us under load, once per chunk per warp otherwise) hides behind the wait and the previous chunk.
-      uint4 pre[8];        // one buffer for both kinds (a launch has a residual OR an act' mask on this path, never both)
+      uint4 pre[CW / 4];   // one buffer for both kinds (a launch has a residual OR an act' mask on this path, never both)
       const int mrow_t = t.m0 + quad * 32 + lane;
       const long long zres = (p.zmode == 1) ? (long long)t.z * p.res_bstride : 0;
       auto prefetch_side = [&](int c0n) {
@@ -512,11 +518,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         if (feat & F_RES) {
           const float* rp = res_v + zres + (long long)mrow_t * ldres_v + n0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pre[j] = ldg128u_nc_if(rp + 4 * j, ok && n0 + 4 * j < Nv);
+          for (int j = 0; j < CW / 4; ++j) pre[j] = ldg128u_nc_if(rp + 4 * j, ok && n0 + 4 * j < Nv);
         } else if (feat & F_DACT) {
           const __nv_bfloat16* dp = p.dact_hi + (long long)mrow_t * p.ld_dact + n0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) pre[j] = ldg128u_nc_if(dp + 8 * j, ok && n0 + 8 * j < Nv);
+          for (int j = 0; j < CW / 8; ++j) pre[j] = ldg128u_nc_if(dp + 8 * j, ok && n0 + 8 * j < Nv);
         }
       };
       if ((feat & F_TMA) && (feat & (F_RES | F_DACT))) prefetch_side(0);
@@ -526,11 +532,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * BN + half * CH;
       const int mbase = t.m0 + quad * 32 + rsub;           // this thread's first row after the transpose
       const int nbase = t.n0 + half * CH + cj * 4;
-      uint32_t r[32];
-      tmem_ld32(taddr0, r);
-      if (feat & F_TMA) {
+      uint32_t r[CW];
+      tmem_ld_chunk<CW>(taddr0, r);
+      if ((feat & F_TMA) || EW == 16) {
         // ---------------------------------------------------------------------------------- TMA-store epilogue
-        // Everything happens in the accumulator's own layout (tcgen05.ld 32x32b: thread = row, 32 consecutive columns
+        // Everything happens in the accumulator's own layout (tcgen05.ld 32x32b: thread = row, CW consecutive columns
         // in registers): bias / row bias / activation / act' mask / residual are applied there, the finished values
         // are written once into this warp's staging tile in the TMA swizzle, and one elected lane issues the
         // cp.async.bulk.tensor store.  TMA clips rows >= M and columns >= N.  No transposed second register pass, no
@@ -539,16 +545,16 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
         const bool row_ok = mrow < Mv;
         const bool warp_rows_ok = t.m0 + quad * 32 < Mv;
 #pragma unroll 1
-        for (int c0 = 0; c0 < CH; c0 += 32) {
+        for (int c0 = 0; c0 < CH; c0 += CW) {
           const int n0 = t.n0 + half * CH + c0;            // first column of the chunk (warp-uniform)
           const bool live = warp_rows_ok && n0 < Nv;
 
           tmem_ld_wait();
-          float v[32];
+          float v[CW];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (c0 + 32 < CH) {
-            tmem_ld32(taddr0 + c0 + 32, r);                // next chunk streams in while this one is processed
+          for (int j = 0; j < CW; ++j) v[j] = __uint_as_float(r[j]);
+          if (c0 + CW < CH) {
+            tmem_ld_chunk<CW>(taddr0 + c0 + CW, r);        // next chunk streams in while this one is processed
           } else {                                         // last read of this accumulator: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
@@ -558,9 +564,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             }
           }
           if (!live) continue;
-          if (feat & F_BIAS) {                             // the same 32 values for every lane: broadcast loads
+          if (feat & F_BIAS) {                             // the same CW values for every lane: broadcast loads
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CW / 4; ++j) {
               const float4 b = ldg128_nc_if(bias_v + n0 + 4 * j, n0 + 4 * j < Nv);
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
@@ -568,19 +574,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           if (feat & F_ROWBIAS) {
             const float* rb = p.rowbias + (long long)(mrow / p.rowbias_div) * p.ld_rowbias + n0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CW / 4; ++j) {
               const float4 b = ldg128_nc_if(rb + 4 * j, row_ok && n0 + 4 * j < Nv);
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
           if (feat & F_ACT) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = (v[j] > 0.f) ? v[j] : pslope * v[j];
+            for (int j = 0; j < CW; ++j) v[j] = (v[j] > 0.f) ? v[j] : pslope * v[j];
           }
           if (feat & F_DACT) {
             const float ds = p.dact_slope;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < CW / 8; ++j) {
               const uint32_t w[4] = {pre[j].x, pre[j].y, pre[j].z, pre[j].w};
 #pragma unroll
               for (int q = 0; q < 4; ++q) {
@@ -592,76 +598,90 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
           }
           if (feat & F_RES) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < CW / 4; ++j) {
               v[4 * j] += __uint_as_float(pre[j].x); v[4 * j + 1] += __uint_as_float(pre[j].y);
               v[4 * j + 2] += __uint_as_float(pre[j].z); v[4 * j + 3] += __uint_as_float(pre[j].w);
             }
           }
           // `pre` is consumed: the next chunk's side inputs fly during the staging / store of this chunk and the first
-          // half of the next one (no second buffer: 168 registers per thread is the ceiling with 10 warps per CTA)
-          if ((feat & (F_RES | F_DACT)) && c0 + 32 < CH) prefetch_side(c0 + 32);
-          // the previous chunk's store must have finished READING the staging tile before it is overwritten
-          if (lane == 0) bulk_wait_read0();
-          __syncwarp();
-          if (feat & F_OUT) {
+          // half of the next one
+          if ((feat & (F_RES | F_DACT)) && c0 + CW < CH) prefetch_side(c0 + CW);
+          {
+            // the previous chunk's store must have finished READING the staging tile before it is overwritten
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
+            // staging rows are CW * 4 (fp32) or CW * 2 (bf16) bytes; 16-byte column chunk c of row `lane` goes to chunk
+            // c ^ swz, swz = the TMA swizzle of that row pitch (128 B: row & 7; 64 B: (row >> 1) & 3; 32 B: (row >> 2) & 1)
+            if (feat & F_OUT) {
+              const uint32_t swf = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts128(stg + lane * 128 + ((j ^ (lane & 7)) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-          } else {                                         // bf16 hi (and lo) planes: 64-byte rows, SWIZZLE_64B
-            uint32_t hi[16];
+              for (int j = 0; j < CW / 4; ++j)
+                sts128(stg + lane * (CW * 4) + ((j ^ swf) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            } else {                                         // bf16 hi (and lo) planes
+              uint32_t hi[CW / 2];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-            const uint32_t sw = (lane >> 1) & 3;
+              for (int j = 0; j < CW / 2; ++j) hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+              const uint32_t sw = CW == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-              sts128(stg + lane * 64 + ((c ^ sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-            if (feat & F_LO) {
+              for (int c = 0; c < CW / 8; ++c)
+                sts128(stg + lane * (CW * 2) + ((c ^ sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+              if (feat & F_LO) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                uint32_t lo[4];
+                for (int c = 0; c < CW / 8; ++c) {
+                  uint32_t lo[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const int j = 4 * c + q;
-                  lo[q] = pack_bf16(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xFFFF0000u));
+                  for (int q = 0; q < 4; ++q) {
+                    const int j = 4 * c + q;
+                    lo[q] = pack_bf16(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xFFFF0000u));
+                  }
+                  sts128(stg + 64 * CW + lane * (CW * 2) + ((c ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
                 }
-                sts128(stg + 2048 + lane * 64 + ((c ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
               }
             }
-          }
-          fence_async_smem();                              // generic-proxy smem writes -> visible to the async proxy (TMA)
-          __syncwarp();
-          if (lane == 0) {
-            const int mw = t.m0 + quad * 32;
-            const int zc = (p.zmode == 1) ? t.z : 0;      // batched: the box never spans two problems (rows >= M clipped)
-            if (feat & F_OUT) {
-              tma_store_3d(&maps.c_out, stg, n0, mw, zc);
-            } else {
-              tma_store_3d(&maps.c_hi, stg, n0, mw, zc);
-              if (feat & F_LO) tma_store_3d(&maps.c_lo, stg + 2048, n0, mw, zc);
+            fence_async_smem();                              // generic-proxy smem writes -> visible to the async proxy (TMA)
+            __syncwarp();
+            if (lane == 0) {
+              const int mw = t.m0 + quad * 32;
+              const int zc = (p.zmode == 1) ? t.z : 0;      // batched: the box never spans two problems (rows >= M clipped)
+              if (feat & F_OUT) {
+                tma_store_3d(&maps.c_out, stg, n0, mw, zc);
+              } else {
+                tma_store_3d(&maps.c_hi, stg, n0, mw, zc);
+                if (feat & F_LO) tma_store_3d(&maps.c_lo, stg + 64 * CW, n0, mw, zc);
+              }
+              bulk_commit();
             }
-            bulk_commit();
           }
           if (feat & F_COLPART) {
-            // column sums over this warp's 32 rows by recursive halving across the lanes (31 shuffles, fixed order):
-            // afterwards lane L holds the sum of column L.  Rows past M do not count.
+            // column sums over this warp's 32 rows by recursive halving across the lanes (fixed order): each level sends
+            // half of the values to the partner lane; once a single value is left (CW = 16: at the last level) the level
+            // is a plain pairwise add.  Afterwards lane L holds the sum of column L (CW = 32) or L >> 1 (CW = 16).
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = row_ok ? v[j] : 0.f;
+            for (int j = 0; j < CW; ++j) v[j] = row_ok ? v[j] : 0.f;
 #pragma unroll
             for (int sft = 16; sft >= 1; sft >>= 1) {
-              const bool upper = (lane & sft) != 0;
+              const int hn = CW == 32 ? sft : sft / 2;     // values left after this level (a function of the unrolled loop
+              if (hn >= 1) {                                // variable only: v[] must stay in registers)
+                const bool upper = (lane & sft) != 0;
 #pragma unroll
-              for (int i = 0; i < sft; ++i) {
-                const float send = upper ? v[i] : v[i + sft];
-                const float keep = upper ? v[i + sft] : v[i];
-                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                for (int i = 0; i < hn; ++i) {
+                  const float send = upper ? v[i] : v[i + hn];
+                  const float keep = upper ? v[i + hn] : v[i];
+                  v[i] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+                }
+              } else {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], sft);
               }
             }
-            if (n0 + lane < Nv) p.colpart[(long long)((t.m0 + quad * 32) >> 5) * p.N + n0 + lane] = v[0];
+            const int col = CW == 32 ? lane : (lane >> 1);
+            if ((CW == 32 || (lane & 1) == 0) && n0 + col < Nv)
+              p.colpart[(long long)((t.m0 + quad * 32) >> 5) * p.N + n0 + col] = v[0];
           }
         }
         continue;      // next tile
       }
+      if constexpr (EW == 8) {
 #pragma unroll 1
       for (int c0 = 0; c0 < CH; c0 += 32) {
         const int n = nbase + c0;
@@ -809,8 +829,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_bf_kernel(const __grid_const
             *reinterpret_cast<float4*>(p.colpart + (long long)((t.m0 + quad * 32) >> 5) * p.N + n) = make_float4(cs[0], cs[1], cs[2], cs[3]);
         }
       }
+      }   // EW == 8: register epilogue
     }
-    if ((feat & F_TMA) && lane == 0) bulk_wait0();         // the staging tile must outlive the last store's read
+    if (((feat & F_TMA) || EW == 16) && lane == 0) bulk_wait0();   // the staging tile must outlive the last store's read
   }
 
   tc_fence_before();
@@ -1081,8 +1102,8 @@ static int make_map(CUtensorMap* m, const void* base, long long inner, long long
 }
 
 // Output map for the TMA-store epilogue: [batch][outer rows][inner elements contiguous], row pitch ld and batch pitch
-// bstride elements, box {32, 32, 1} (a box never spans two problems of a batch).
-static int make_out_map(CUtensorMap* m, const void* base, bool is_f32, long long inner, long long outer, long long ld,
+// bstride elements, box {box_cols, 32, 1} (a box never spans two problems of a batch).
+static int make_out_map(CUtensorMap* m, const void* base, bool is_f32, int box_cols, long long inner, long long outer, long long ld,
                         long long batch = 1, long long bstride = 0) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
@@ -1096,11 +1117,14 @@ static int make_out_map(CUtensorMap* m, const void* base, bool is_f32, long long
   }
   cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)ld * esz, (cuuint64_t)bstride * esz};
-  cuuint32_t box[3] = {32u, 32u, 1u};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32u, 1u};
   cuuint32_t estr[3] = {1u, 1u, 1u};
+  const int row_bytes = box_cols * esz;        // 128 / 64 / 32: the staging tile is written in the swizzle of its row pitch
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(m, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, is_f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("gemm_bf16: cuTensorMapEncodeTiled (output) failed (%d) base=%p inner=%lld outer=%lld ld=%lld", (int)r, base, inner,
               outer, ld);
@@ -1115,14 +1139,22 @@ static bool tma_epi_enabled() {      // read per call: the parity test flips it 
   return !(e && e[0] == '0');
 }
 
-template <int NSPLIT, int BN, bool CTA2>
+static bool epi16_enabled(bool colsum) {
+  const char* e = getenv("DOST_GEMM_EPI16");
+  if (e && e[0] == '0') return false;
+  if (e && e[0] == '2') return true;
+  return !colsum;
+}
+
+template <int NSPLIT, int BN, bool CTA2, int EW = 8>
 static int launch(const Maps& maps, const Params& p, cudaStream_t st) {
+  constexpr int kThreads = (EW + 2) * 32;
   constexpr int A_BYTES = BM * BK * 2, B_BYTES = (CTA2 ? BN / 2 : BN) * BK * 2;
   constexpr int STAGE_BYTES = (NSPLIT == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
   constexpr int NSTAGE_RAW = (kSmemBudget - kEpiBytes) / STAGE_BYTES;
   constexpr int NSTAGE = NSTAGE_RAW < kMaxStages ? NSTAGE_RAW : kMaxStages;
   const int smem = NSTAGE * STAGE_BYTES + kEpiBytes + 1024;
-  auto kern = gemm_bf_kernel<NSPLIT, BN, CTA2>;
+  auto kern = gemm_bf_kernel<NSPLIT, BN, CTA2, EW>;
   static PerDevice cfg_once;
   if (bool* cfg_flag = cfg_once.pending()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1317,6 +1349,7 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
 
   // ---- TMA-store epilogue: exactly one kind of output, no pre-activation copy / accumulation / split-K / ragged rows
   p.tma_epi = 0;
+  bool ew16 = false;
   maps.c_out = maps.b_hi;
   maps.c_hi = maps.b_hi;
   maps.c_lo = maps.b_hi;
@@ -1324,19 +1357,26 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
       ((h->out != nullptr) != (h->out_hi != nullptr)) && h->M >= 32 && h->N >= 32 && !(h->dact_hi && h->residual) &&
       (!h->dact_hi || (al16(h->dact_hi) && h->ld_dact % 8 == 0))) {
     int rc2 = DOST_OK;
+    // CTA-pair launches run 16 epilogue warps on 16-column chunks (DOST_GEMM_EPI16=0: 8 warps on 32-column chunks; =2:
+    // also with fused column sums, where 16 warps measured 16 % slower: 0.400 -> 0.464 ms at the FFN's fc2 input gradient)
+    ew16 = pairs && epi16_enabled(h->colsum != nullptr);
+    const int bc = ew16 ? 16 : 32;
     if (h->out) {     // (batched problems: fp32 stores only, checked above)
-      rc2 = make_out_map(&maps.c_out, h->out, true, h->N, h->M, h->ldc, batch, h->c_bstride);
+      rc2 = make_out_map(&maps.c_out, h->out, true, bc, h->N, h->M, h->ldc, batch, h->c_bstride);
     } else if (al16(h->out_hi) && al16(h->out_lo) && h->ld_op % 8 == 0) {
-      rc2 = make_out_map(&maps.c_hi, h->out_hi, false, h->N, h->M, h->ld_op);
-      if (rc2 == DOST_OK && h->out_lo) rc2 = make_out_map(&maps.c_lo, h->out_lo, false, h->N, h->M, h->ld_op);
+      rc2 = make_out_map(&maps.c_hi, h->out_hi, false, bc, h->N, h->M, h->ld_op);
+      if (rc2 == DOST_OK && h->out_lo) rc2 = make_out_map(&maps.c_lo, h->out_lo, false, bc, h->N, h->M, h->ld_op);
     } else {
       rc2 = DOST_ERR_ARG;
     }
     if (rc2 == DOST_OK) p.tma_epi = 1;       // (a shape the encoder rejects simply keeps the register epilogue)
+    else ew16 = false;
   }
 
   int rc;
-  if (pairs) {
+  if (pairs && ew16) {
+    rc = split3 ? launch<3, 256, true, 16>(maps, p, st) : launch<1, 256, true, 16>(maps, p, st);
+  } else if (pairs) {
     rc = split3 ? launch<3, 256, true>(maps, p, st) : launch<1, 256, true>(maps, p, st);
   } else if (split3) {
     rc = bn == 64 ? launch<3, 64, false>(maps, p, st)

@@ -888,10 +888,11 @@ def test_planes_gemm_batched_and_ragged(prec, tol):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("epi16", ["2", "0"])
 @pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
 @pytest.mark.parametrize("M,N,K,b_mode", [(256, 256, 256, "KC"), (1000, 512, 768, "KC"), (333, 72, 200, "KC"), (4100, 1024, 256, "MC"),
                                           (130, 260, 64, "KC"), (5000, 256, 1024, "MC"), (77, 40, 48, "KC"), (32, 32, 64, "KC")])
-def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, b_mode, monkeypatch):
+def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, b_mode, epi16, monkeypatch):
     """The TMA-store epilogue (values finished in the accumulator layout, staged in the TMA swizzle, cp.async.bulk.tensor
     stores; csrc/gemm_bf.cu) must reproduce the register epilogue BIT FOR BIT: same accumulators, same fp32 operations per
     element (bias, row-group bias, activation, act' mask, residual, bf16 hi/lo split); ragged M / N tails are clipped by
@@ -903,6 +904,11 @@ def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, 
     bias, res = torch.randn(N, device=DEV), torch.randn(M, N, device=DEV)
     rb = torch.randn((M + 6) // 7, N, device=DEV)
     saved = torch.randn(M, N, device=DEV)
+
+    # CTA-pair launches (M > 128 and N > 128) have two TMA-store variants: 16 epilogue warps on 16-column chunks ("2": for
+    # every launch, also those with fused column sums) and 8 warps on 32-column chunks ("0"); both must equal the
+    # register epilogue
+    monkeypatch.setenv("DOST_GEMM_EPI16", epi16)
 
     def run(tma):
         monkeypatch.setenv("DOST_GEMM_TMA_EPI", "1" if tma else "0")
