@@ -1352,6 +1352,28 @@ class _CrossAttention(torch.autograd.Function):
         return d_q, dkv, dph, d_resid, None, None, None, None
 
 
+def fused_attention_ok(H: int, max_keys: int, drop_p: float) -> bool:
+    """True when the single-kernel attention forward (csrc/attn_fused.cu: QK^T -> fp32 softmax -> PK with the scores in
+    TMEM) covers this call: at most 256 keys per sequence, H in {64, 128, 192, 256}, no attention dropout (the dropout
+    path keeps the GEMM + softmax + GEMM formulation).  DOST_NO_ATTN_FUSED=1 switches it off."""
+    return (drop_p == 0 and H % 64 == 0 and 64 <= H <= 256 and 1 <= max_keys <= 256 and _PRECISION != L.PREC_FMA
+            and not L.switch("DOST_NO_ATTN_FUSED"))
+
+
+def _fused_attention_fwd(qp: Planes, kp: Planes, k_rows: int, S: int, Lq: int, Lk: int, H: int, rowoff, count, nmax, max_keys: int,
+                         resid2d, res_seq_stride: int, out2d, pp: Optional[Planes]):
+    L.check(L.lib().dost_attn_fused_fwd(L.p(qp.hi), L.p(qp.lo), qp.ld, L.p(kp.hi), L.p(kp.lo), kp.ld, k_rows, S, Lq, Lk, H,
+                                        L.p(rowoff), L.p(count), L.p(nmax), max_keys, float(H) ** -0.5, L.p(resid2d),
+                                        res_seq_stride, L.p(out2d), L.p(pp.hi) if pp is not None else None,
+                                        L.p(pp.lo) if pp is not None else None, pp.ld if pp is not None else 0, _PRECISION,
+                                        L.stream()), "attn_fused_fwd")
+
+
+def _ds_from_planes(pp: Planes, dP2d: torch.Tensor, rows: int, cols: int, scale: float, dsp: Planes):
+    L.check(L.lib().dost_softmax_bwd_from_planes(L.p(pp.hi), L.p(pp.lo), pp.ld, L.p(dP2d), dP2d.stride(0), rows, cols, scale,
+                                                 L.p(dsp.hi), L.p(dsp.lo), dsp.ld, L.stream()), "softmax_bwd_from_planes")
+
+
 class _CrossAttentionTC(torch.autograd.Function):
     """The same attention with its contractions on the tensor cores: ragged batched GEMMs (one problem per sequence, the
     keys of its crystal addressed by a row offset into one extended key plane that carries a phantom-key row per
@@ -1379,6 +1401,20 @@ class _CrossAttentionTC(torch.autograd.Function):
         kvp = empty_planes(N + B, H, dev, _with_lo())
         L.check(lib.dost_xattn_kv_ext_build(L.p(kv), L.p(phantom), L.p(graph.batch), L.p(graph.ptr), N, B, H, L.p(kvp.hi), L.p(kvp.lo),
                                             kvp.ld, L.stream()), "xattn_kv_ext_build")
+        out = torch.empty(S, T, H, dtype=torch.float32, device=dev)
+        r2 = resid.view(-1, H)
+        ctx.graph, ctx.prec, ctx.npad = graph, _PRECISION, npad
+        ctx.bcast_q, ctx.bcast_r, ctx.T, ctx.S = bcast_q, resid.dim() == 2, T, S
+        ctx.drop_p, ctx.seed = drop_p, seed
+        ctx.fused = fused_attention_ok(H, graph.nmax_host + 1, drop_p)
+        if ctx.fused:
+            # one kernel: scores stay in TMEM, the probabilities leave only as the operand planes the backward needs
+            pp = empty_planes(S * T, npad, dev, _with_lo()) if any(ctx.needs_input_grad[:4]) else None
+            _fused_attention_fwd(qp, kvp, N + B, S, T, 0, H, ptr_ext, n_ext, graph.nmax, graph.nmax_host + 1, r2,
+                                 0 if resid.dim() == 2 else T * H, out.view(S * T, H), pp)
+            if pp is not None:
+                ctx.save_for_backward(kv, phantom, None, None, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
+            return out
         scores = torch.empty(S * T, npad, dtype=torch.float32, device=dev)
         gemm_planes(M=T, N=npad, K=H, a=[qp], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=scores, batch=S,
                     a_bstride=T * qp.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
@@ -1387,15 +1423,10 @@ class _CrossAttentionTC(torch.autograd.Function):
         scale = float(H) ** -0.5
         L.check(lib.dost_xattn_softmax_fwd(L.p(scores), L.p(graph.ptr), L.p(graph.nmax), S * T, B, T, npad, scale, L.p(pp.hi),
                                            L.p(pp.lo), pp.ld, L.p(lse), drop_p, seed, L.stream()), "xattn_softmax_fwd")
-        out = torch.empty(S, T, H, dtype=torch.float32, device=dev)
-        r2 = resid.view(-1, H)
         gemm_planes(M=T, N=H, K=npad, a=[pp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=out.view(S * T, H), residual=r2,
                     batch=S, a_bstride=T * pp.ld, c_bstride=T * H, res_bstride=(0 if resid.dim() == 2 else T * H),
                     b_rowoff=ptr_ext)
         ctx.save_for_backward(kv, phantom, scores, lse, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
-        ctx.graph, ctx.prec, ctx.npad = graph, _PRECISION, npad
-        ctx.bcast_q, ctx.bcast_r, ctx.T, ctx.S = bcast_q, resid.dim() == 2, T, S
-        ctx.drop_p, ctx.seed = drop_p, seed
         return out
 
     @staticmethod
@@ -1418,9 +1449,12 @@ class _CrossAttentionTC(torch.autograd.Function):
             gemm_planes(M=T, N=npad, K=H, a=[dop], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=dP, batch=S,
                         a_bstride=T * dop.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
             dsp = empty_planes(S * T, npad, dev, _with_lo())
-            L.check(lib.dost_xattn_softmax_bwd(L.p(scores), L.p(lse), L.p(dP), L.p(g.ptr), L.p(g.nmax), S * T, B, T, npad,
-                                               float(H) ** -0.5, L.p(dsp.hi), L.p(dsp.lo), dsp.ld, ctx.drop_p, ctx.seed,
-                                               L.stream()), "xattn_softmax_bwd")
+            if ctx.fused:      # probabilities from their saved planes (the phantom column behaves like one key of its total mass)
+                _ds_from_planes(pp, dP, S * T, npad, float(H) ** -0.5, dsp)
+            else:
+                L.check(lib.dost_xattn_softmax_bwd(L.p(scores), L.p(lse), L.p(dP), L.p(g.ptr), L.p(g.nmax), S * T, B, T, npad,
+                                                   float(H) ** -0.5, L.p(dsp.hi), L.p(dsp.lo), dsp.ld, ctx.drop_p, ctx.seed,
+                                                   L.stream()), "xattn_softmax_bwd")
             # dQ = dS k
             dq = torch.empty(S, T, H, dtype=torch.float32, device=dev)
             gemm_planes(M=T, N=H, K=npad, a=[dsp], a_mode=L.KC, b=kvp, b_mode=L.MC, b_rows=N + B, out=dq.view(S * T, H), batch=S,
@@ -1473,12 +1507,23 @@ class _SelfAttention(torch.autograd.Function):
         q, k, resid = q.contiguous(), k.contiguous(), resid.contiguous()
         dev, dtype = q.device, q.dtype
         Lp = (Lk + 3) // 4 * 4          # padded row length of the score matrices: keeps 16-byte vector loads legal
-        scores = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
         ctx.on_planes = tc_active(q) and H % 8 == 0 and Lq * Lk * H >= (1 << 18) and not L.switch("DOST_NO_ATTNPLANES")
         if ctx.on_planes:
             # the four batched contractions on the TMA-fed tensor-core kernel (3-D tensor maps, one batch per sequence)
             qp = qpl if qpl is not None else split_planes(q.view(S * Lq, H))
             kp = kpl if kpl is not None else split_planes(k.view(S * Lk, H))
+            ctx.drop_p, ctx.seed, ctx.prec = drop_p, seed, _PRECISION
+            ctx.dims = (S, Lq, Lk, H, Lp)
+            ctx.fused = fused_attention_ok(H, Lk, drop_p)
+            if ctx.fused:
+                out = torch.empty(S, Lq, H, dtype=dtype, device=dev)
+                pdp = empty_planes(S * Lq, Lk, dev, _with_lo()) if any(ctx.needs_input_grad[:3]) else None
+                _fused_attention_fwd(qp, kp, S * Lk, S, Lq, Lk, H, None, None, None, Lk, resid.view(S * Lq, H), Lq * H,
+                                     out.view(S * Lq, H), pdp)
+                if pdp is not None:
+                    ctx.save_for_backward(None, None, *_planes_save(qp), *_planes_save(kp), *_planes_save(pdp))
+                return out
+            scores = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
             gemm_planes(M=Lq, N=Lp, K=H, a=[qp], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=scores.view(S * Lq, Lp),
                         batch=S, a_bstride=Lq * qp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
             pd = torch.empty_like(scores) if drop_p > 0 else scores
@@ -1490,9 +1535,8 @@ class _SelfAttention(torch.autograd.Function):
                         residual=resid.view(S * Lq, H), batch=S, a_bstride=Lq * pdp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * H,
                         res_bstride=Lq * H)
             ctx.save_for_backward(scores, pd if drop_p > 0 else None, *_planes_save(qp), *_planes_save(kp), *_planes_save(pdp))
-            ctx.drop_p, ctx.seed, ctx.prec = drop_p, seed, _PRECISION
-            ctx.dims = (S, Lq, Lk, H, Lp)
             return out
+        scores = torch.empty(S, Lq, Lp, dtype=dtype, device=dev)
         gemm_raw(M=Lq, N=Lk, K=H, a=[(q.view(S * Lq, H), None)], a_mode=L.KC, b=k.view(S * Lk, H), b_mode=L.KC,
                  out=scores, batch=S, a_bstride=Lq * H, b_bstride=Lk * H, c_bstride=Lq * Lp, ldc=Lp)
         pd = torch.empty_like(scores) if drop_p > 0 else scores
@@ -1542,7 +1586,7 @@ class _SelfAttention(torch.autograd.Function):
 def _self_attention_backward_planes(ctx, d_out):
     prob, pd, qh, ql, kh, kl, ph, pl_ = ctx.saved_tensors
     S, Lq, Lk, H, Lp = ctx.dims
-    dev = prob.device
+    dev = qh.device
     scale = float(H) ** -0.5
     qp, kp = Planes(qh, ql, S * Lq, H), Planes(kh, kl, S * Lk, H)
     pdp = Planes(ph, pl_, S * Lq, Lk)
@@ -1553,8 +1597,11 @@ def _self_attention_backward_planes(ctx, d_out):
     gemm_planes(M=Lq, N=Lp, K=H, a=[dop], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=dpd.view(S * Lq, Lp), batch=S,
                 a_bstride=Lq * dop.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
     dsp = empty_planes(S * Lq, Lk, dev, _with_lo())              # dS only ever feeds GEMMs: planes, no fp32 copy
-    L.check(L.lib().dost_softmax_bwd_planes(L.p(prob), L.p(dpd), None, S * Lq, Lk, Lp, scale, ctx.drop_p, ctx.seed, L.p(dsp.hi),
-                                            L.p(dsp.lo), dsp.ld, L.stream()), "softmax_bwd_planes")
+    if ctx.fused:
+        _ds_from_planes(pdp, dpd.view(S * Lq, Lp), S * Lq, Lk, scale, dsp)
+    else:
+        L.check(L.lib().dost_softmax_bwd_planes(L.p(prob), L.p(dpd), None, S * Lq, Lk, Lp, scale, ctx.drop_p, ctx.seed, L.p(dsp.hi),
+                                                L.p(dsp.lo), dsp.ld, L.stream()), "softmax_bwd_planes")
     # dQ = dS k
     dq = torch.empty(S, Lq, H, dtype=torch.float32, device=dev)
     gemm_planes(M=Lq, N=H, K=Lk, a=[dsp], a_mode=L.KC, b=kp, b_mode=L.MC, out=dq.view(S * Lq, H), batch=S,

@@ -989,3 +989,94 @@ def test_cross_attention_dropout_on_tensor_cores_equals_fma_kernels(reps):
     with ops.precision("bf16x3"):
         base = ops.cross_attention(q0, kv0, ph0, q0, gr, S, 0.0, 0)
     assert relerr(res["tc"][0], base) > 1e-2
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def _switch(monkeypatch, name):
+    """A DOST_NO_* bisect switch set for the duration of the block (the package caches the switches per process)."""
+    monkeypatch.setenv(name, "1")
+    L.reload_switches()
+    try:
+        yield
+    finally:
+        monkeypatch.delenv(name)
+        L.reload_switches()
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 2e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("S,Lq,Lk,H", [(5, 201, 201, 256), (3, 51, 51, 64), (4, 17, 40, 128), (2, 300, 256, 192), (1, 128, 1, 64),
+                                       (300, 129, 33, 128)])
+def test_fused_attention_dense(prec, tol, S, Lq, Lk, H, monkeypatch):
+    """csrc/attn_fused.cu (QK^T -> fp32 softmax in TMEM -> PK in one kernel, layers/multihead_attention.py:68-72) against
+    the fp64 oracle, and against the three-kernel formulation it replaces: outputs and all gradients (the backward reads
+    the probabilities back from the planes the fused kernel saved).  Query tiles with a ragged tail (Lq % 128 != 0), key
+    chunks with a tail (Lk % 32 != 0), one key, every supported width, more work items than SMs."""
+    q, k = _leaf(_rand(S, Lq, H, dtype=torch.float32, seed=1)), _leaf(_rand(S, Lk, H, dtype=torch.float32, seed=2))
+    r = _leaf(_rand(S, Lq, H, dtype=torch.float32, seed=3))
+    with ops.precision(prec):
+        assert ops.fused_attention_ok(H, Lk, 0.0)
+        n0 = L.launch_count()
+        with torch.no_grad():
+            o_inf = ops.self_attention(q, k, r)
+        # planes of q and k (2 launches) + ONE attention kernel; nothing else
+        assert L.launch_count() - n0 == 3
+        o1, g1 = _grads(lambda: ops.self_attention(q, k, r), [q, k, r])
+        assert torch.equal(o_inf, o1[0])                 # saving the probabilities does not change the output
+        with _switch(monkeypatch, "DOST_NO_ATTN_FUSED"):
+            o3, g3 = _grads(lambda: ops.self_attention(q, k, r), [q, k, r])
+    o2, g2 = _grads(lambda: r + O.attention(q, k), [q, k, r])
+    for a_, b_ in zip(o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol
+    for a_, b_ in zip(o1 + g1, o3 + g3):                 # same arithmetic up to exp2 / summation order
+        assert relerr(a_, b_) < (2e-5 if prec == "bf16x3" else 2e-2)
+
+
+@pytest.mark.parametrize("prec,tol", [("bf16x3", 1e-4), ("bf16", 5e-2)])
+@pytest.mark.parametrize("H,broadcast,T,reps,sizes", [(128, False, 201, 1, None), (256, True, 201, 1, None), (256, False, 201, 2, None),
+                                                      (128, False, 70, 1, [150, 40, 254, 7, 1]), (128, False, 130, 2, [3, 64, 31, 32])])
+def test_fused_attention_ragged(prec, tol, H, broadcast, T, reps, sizes, monkeypatch):
+    """The same kernel on ragged key sets (energy -> atom cross attention, DOSTransformer.py:61-77): per-sequence row
+    offsets into one extended key plane, the phantom column weighted by its multiplicity inside the softmax, sequences
+    with fewer key chunks than the batch maximum, 2 sequences per crystal.  Against the padded dense reference and
+    against the GEMM + softmax + GEMM formulation."""
+    from dostransformer_b200.synthetic import make_edos_batch
+    if sizes is None:
+        g = make_edos_batch(6, seed=31, mean_atoms=9.0, max_atoms=50)
+    else:
+        g = make_edos_batch(len(sizes), seed=31, sizes=torch.tensor(sizes))
+    gr = ops.build_graph(g.edge_index.to(DEV), g.batch.to(DEV), g.system.to(DEV), nmax_hint=g.max_num_nodes)
+    B = gr.B
+    S = reps * B
+    with ops.precision(prec):
+        assert ops.fused_attention_ok(H, g.max_num_nodes + 1, 0.0)
+    xn = _leaf(_rand(gr.N, H, dtype=torch.float32, seed=1))
+    q = _leaf(_rand(T, H, dtype=torch.float32, seed=2)) if broadcast else _leaf(_rand(S, T, H, dtype=torch.float32, seed=2))
+    gam, bet = _leaf(_rand(H, dtype=torch.float32, seed=3)), _leaf(_rand(H, dtype=torch.float32, seed=4))
+    bd = g.batch.to(DEV)
+
+    def mine():
+        kv = ops.layer_norm(xn, gam, bet)
+        ql = ops.layer_norm(q, gam, bet, want_planes=q.dim() == 3)
+        out = ops.cross_attention(ql, kv, bet, q, gr, S)
+        assert type(out.grad_fn).__name__.startswith("_CrossAttentionTC")
+        return out
+
+    def ref():
+        if broadcast:
+            return _dense_cross_ref(q[None].expand(B, T, H), xn, gam, bet, bd, H)
+        return torch.cat([_dense_cross_ref(q[i * B:(i + 1) * B], xn, gam, bet, bd, H) for i in range(reps)], 0)
+
+    with ops.precision(prec):
+        o1, g1 = _grads(mine, [xn, q, gam, bet])
+        with _switch(monkeypatch, "DOST_NO_ATTN_FUSED"):
+            o3, g3 = _grads(mine, [xn, q, gam, bet])
+    o2, g2 = _grads(ref, [xn, q, gam, bet])
+    for nm, a_, b_ in zip(["out", "dx", "dq", "dgamma", "dbeta"], o1 + g1, o2 + g2):
+        assert relerr(a_, b_) < tol, (nm, relerr(a_, b_))
+    for nm, a_, b_ in zip(["out", "dx", "dq", "dgamma", "dbeta"], o1 + g1, o3 + g3):
+        assert relerr(a_, b_) < (3e-5 if prec == "bf16x3" else 3e-2), (nm, relerr(a_, b_))
+    torch.cuda.synchronize()
+    L.poll_device_errors()
