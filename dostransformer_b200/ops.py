@@ -197,6 +197,12 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
         host = int(nmax_override) if nmax_hint is not None else None
     elif nmax_hint is not None:
         host = int(nmax_hint)
+    if host is None and phantoms and B > 0 and not L.switch("DOST_NO_NMAX_SYNC") and not torch.cuda.is_current_stream_capturing():
+        # A batch collated elsewhere (a stock PyG Batch from main_eDOS.py:54 carries no max_num_nodes): ONE device->host
+        # read of the padding length buys the tensor-core attention path, whose buffers are sized on the host.  (The
+        # reference reads back twice per forward: len(batch.unique()) DOSTransformer.py:118 and to_dense_batch's max().)
+        # Batches from this package's collate / sharder / synthetic generators carry the hint and never get here.
+        host = int(nmax.item())
     return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host)
 
 

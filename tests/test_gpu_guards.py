@@ -37,8 +37,9 @@ def test_stale_padding_length_is_rejected():
     with pytest.raises(ValueError, match="stale data-parallel padding length"):
         ops.build_graph(g.edge_index, g.batch, g.system, nmax_override=g.max_num_nodes - 1, nmax_hint=g.max_num_nodes)
     # without a host hint the device value becomes max(override, measured): never below the batch's own maximum
+    # (and the padding length is read back once, so that the batch still takes the host-sized tensor-core attention)
     gr = ops.build_graph(g.edge_index, g.batch, g.system, nmax_override=2)
-    assert int(gr.nmax.item()) == g.max_num_nodes and gr.nmax_host is None
+    assert int(gr.nmax.item()) == g.max_num_nodes == gr.nmax_host
     gr = ops.build_graph(g.edge_index, g.batch, g.system, nmax_override=g.max_num_nodes + 7, nmax_hint=g.max_num_nodes)
     assert int(gr.nmax.item()) == g.max_num_nodes + 7 == gr.nmax_host
 
@@ -134,3 +135,32 @@ def test_model_on_a_non_current_device():
     assert b.device == dev1 and torch.equal(a.cpu(), b.cpu())
     with pytest.raises(RuntimeError, match="current device"):
         ops.split_planes(torch.randn(8, 8, device=dev1))
+
+
+def test_batch_without_padding_hint_takes_the_tensor_core_attention(monkeypatch):
+    """A stock PyG Batch (main_eDOS.py:54) has no max_num_nodes: build_graph reads the padding length back once and the
+    model runs the same kernels - bitwise the same outputs - as with the collate's hint; DOST_NO_NMAX_SYNC=1 keeps the
+    step free of device->host reads and falls back to the FMA-pipe attention (same results to the bf16x3 floor)."""
+    from dostransformer_b200.embedder_eDOS.DOSTransformer import DOSTransformer
+    torch.manual_seed(0)
+    m = DOSTransformer(3, 2, 200, 41, 2, 128, torch.device(DEV), 0.0, precision="bf16x3").to(DEV).eval()
+    g = make_edos_batch(6, seed=5, mean_atoms=9.0).to(DEV)
+    with torch.no_grad():
+        want = m(g)[0]
+        hint = g.max_num_nodes
+        del g.max_num_nodes
+        g._keys.remove("max_num_nodes")
+        assert getattr(g, "max_num_nodes", None) is None
+        got = m(g)[0]
+        assert torch.equal(got, want)
+        gr = ops.build_graph(g.edge_index, g.batch, g.system)
+        assert gr.nmax_host == hint
+        monkeypatch.setenv("DOST_NO_NMAX_SYNC", "1")
+        L.reload_switches()
+        try:
+            assert ops.build_graph(g.edge_index, g.batch, g.system).nmax_host is None
+            fma = m(g)[0]
+        finally:
+            monkeypatch.delenv("DOST_NO_NMAX_SYNC")
+            L.reload_switches()
+        assert (fma - want).abs().max() / want.abs().max() < 1e-4
