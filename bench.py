@@ -326,6 +326,57 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
                               "achieved": nbytes / sec / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                               "frac": nbytes / sec / 1e9 / pk["hbm"], "traffic": None, "algorithmic_bytes_per_launch": nbytes,
                               "launch_ms": sec * 1e3}
+    # fused attention forward (csrc/attn_fused.cu): the T x T energy self attention of the 2 B sequences, and the ragged
+    # energy -> atom cross attention of the same batch.  Algorithmic FLOPs: 2 contractions x 2 Lq Lk H per sequence (the
+    # cross attention: Lk = the crystal's own atoms + 1 phantom column).
+    if precision != "fp32" and ops.fused_attention_ok(HIDDEN, T, 0.0):
+        S2 = 2 * B
+        del xs
+        with ops.precision(precision):
+            qs = [torch.randn(S2, T, HIDDEN, device=dev) for _ in range(2)]
+            ks = [torch.randn(S2, T, HIDDEN, device=dev) for _ in range(2)]
+            for t in qs + ks:
+                t._dost_planes = ops.split_planes(t.view(S2 * T, HIDDEN))
+            it3 = {"i": 0}
+
+            def sa():
+                it3["i"] += 1
+                with ops.precision(precision), torch.no_grad():
+                    ops.self_attention(qs[it3["i"] % 2], ks[it3["i"] % 2], qs[(it3["i"] + 1) % 2])
+
+            sec = time_kernel(sa, iters=10)
+            fl = 4.0 * S2 * T * T * HIDDEN
+            mult = 3 if precision == "bf16x3" else 1
+            out["roofline_attention"] = {
+                "kernel": "fa::attn_fwd_kernel (QK^T -> fp32 softmax in TMEM -> PK, one kernel), energy self attention [2B, 201, 256]",
+                "bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": fl / sec / 1e12 / pk["tensor"],
+                "traffic": None, "algorithmic_flops_per_launch": fl, "launch_ms": sec * 1e3,
+                "tensor_pipe_frac": fl * mult / sec / 1e12 / pk["tensor"],
+                "hbm_gbytes_per_s": 3.0 * S2 * T * HIDDEN * 4 / sec / 1e9,
+                "note": "201 queries / keys occupy 256-wide tiles (62 % of the issued MMA work is algorithmic); q, residual and out "
+                        "are the only HBM traffic (no score matrix); the three-kernel formulation it replaces is timed next to it",
+            }
+            os.environ["DOST_NO_ATTN_FUSED"] = "1"
+            L.reload_switches()
+            try:
+                out["roofline_attention"]["unfused_launch_ms"] = time_kernel(sa, iters=10) * 1e3
+            finally:
+                os.environ.pop("DOST_NO_ATTN_FUSED", None)
+                L.reload_switches()
+            kv, ph = torch.randn(gr.N, HIDDEN, device=dev), torch.randn(HIDDEN, device=dev)
+            gr2 = ops.build_graph(g.edge_index.to(dev), g.batch.to(dev), g.system.to(dev), nmax_hint=g.max_num_nodes)
+
+            def xa():
+                it3["i"] += 1
+                with ops.precision(precision), torch.no_grad():
+                    ops.cross_attention(qs[it3["i"] % 2], kv, ph, qs[(it3["i"] + 1) % 2], gr2, S2)
+
+            sec = time_kernel(xa, iters=10)
+            nk = (torch.bincount(g.batch) + 1).double().sum().item() * 2          # keys (atoms + phantom column) over the 2 B sequences
+            out["roofline_attention"]["cross_attention"] = {
+                "launch_ms": sec * 1e3, "tflops": 4.0 * T * nk * HIDDEN / sec / 1e12, "mean_keys_per_sequence": nk / S2,
+                "note": "ragged keys (mean 25 per crystal) against 128-query tiles: bound by the q / residual / out streams, "
+                        + f"{3.0 * S2 * T * HIDDEN * 4 / sec / 1e9:.0f} GB/s of {pk['hbm']:.0f}; includes the key-plane build kernel"}
     return out
 
 
