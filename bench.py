@@ -329,7 +329,9 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
     # fused attention forward (csrc/attn_fused.cu): the T x T energy self attention of the 2 B sequences, and the ragged
     # energy -> atom cross attention of the same batch.  Algorithmic FLOPs: 2 contractions x 2 Lq Lk H per sequence (the
     # cross attention: Lk = the crystal's own atoms + 1 phantom column).
-    if precision != "fp32" and ops.fused_attention_ok(HIDDEN, T, 0.0):
+    with ops.precision(precision):
+        fused_ok = precision != "fp32" and ops.fused_attention_ok(HIDDEN, T, 0.0)
+    if fused_ok:
         S2 = 2 * B
         del xs
         with ops.precision(precision):
