@@ -253,6 +253,13 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t sr
                "r"(src)
                : "memory");
 }
+// out += tile: the TMA reduction store (fp32 add performed at the L2; every output element belongs to exactly one tile, so the
+// result is old + new in a fixed order)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(c2), "r"(src)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -645,7 +652,8 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
               const int mw = t.m0 + quad * 32;
               const int zc = (p.zmode == 1) ? t.z : 0;      // batched: the box never spans two problems (rows >= M clipped)
               if (feat & F_OUT) {
-                tma_store_3d(&maps.c_out, stg, n0, mw, zc);
+                if (feat & F_ACC) tma_reduce_add_3d(&maps.c_out, stg, n0, mw, zc);
+                else tma_store_3d(&maps.c_out, stg, n0, mw, zc);
               } else {
                 tma_store_3d(&maps.c_hi, stg, n0, mw, zc);
                 if (feat & F_LO) tma_store_3d(&maps.c_lo, stg + 64 * CW, n0, mw, zc);
@@ -1347,13 +1355,14 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   DOST_REQUIRE(!h->out_hi || (((uintptr_t)h->out_hi & 7) == 0 && ((uintptr_t)h->out_lo & 7) == 0 && h->ld_op % 4 == 0),
                "gemm_bf16: output plane alignment");
 
-  // ---- TMA-store epilogue: exactly one kind of output, no pre-activation copy / accumulation / split-K / ragged rows
+  // ---- TMA-store epilogue: exactly one kind of output, no pre-activation copy / split-K / ragged rows (an accumulating fp32
+  // output becomes a TMA reduction store)
   p.tma_epi = 0;
   bool ew16 = false;
   maps.c_out = maps.b_hi;
   maps.c_hi = maps.b_hi;
   maps.c_lo = maps.b_hi;
-  if (tma_epi_enabled() && split == 1 && !h->out_pre && !h->accumulate && !p.c_rowoff && !p.c_rowlim &&
+  if (tma_epi_enabled() && split == 1 && !h->out_pre && !(h->accumulate && h->out_hi) && !p.c_rowoff && !p.c_rowlim &&
       ((h->out != nullptr) != (h->out_hi != nullptr)) && h->M >= 32 && h->N >= 32 && !(h->dact_hi && h->residual) &&
       (!h->dact_hi || (al16(h->dact_hi) && h->ld_dact % 8 == 0))) {
     int rc2 = DOST_OK;

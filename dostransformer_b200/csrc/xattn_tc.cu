@@ -73,6 +73,37 @@ __global__ void __launch_bounds__(256) kv_ext_split_kernel(const float* __restri
     *reinterpret_cast<float4*>(dst + c) = __ldg(reinterpret_cast<const float4*>(dext + src * H + c));
 }
 
+// Key gradients computed per SEQUENCE into a padded buffer dpad [reps * B][npad][H] (plain batched GEMMs with TMA / reduction
+// stores instead of ragged accumulating ones) -> gradient of the atoms (sum over the `reps` sequences of a crystal, fixed
+// order) and of the phantom key (row n_b of every block).  One warp per output row; H % 128 == 0.
+__global__ void __launch_bounds__(256) kv_pad_split_kernel(const float* __restrict__ dpad, int npad, int reps,
+                                                           const int* __restrict__ batch, const int* __restrict__ ptr, long long N,
+                                                           int B, int H, float* __restrict__ dkv, float* __restrict__ dbeta_rows) {
+  const int lane = threadIdx.x & 31;
+  const long long r = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (r >= N + B) return;
+  int b, j;
+  float* dst;
+  if (r < N) {
+    b = __ldg(batch + r);
+    j = (int)(r - __ldg(ptr + b));
+    dst = dkv + r * H;
+  } else {
+    b = (int)(r - N);
+    j = __ldg(ptr + b + 1) - __ldg(ptr + b);      // the phantom row follows the crystal's atoms
+    dst = dbeta_rows + (long long)b * H;
+  }
+  const bool inside = j < npad;                   // (a crystal larger than the padding length was reported by the forward)
+  for (int c = lane * 4; c < H; c += 128) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int rep = 0; rep < reps && inside; ++rep) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(dpad + (((long long)rep * B + b) * npad + j) * H + c));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(dst + c) = acc;
+  }
+}
+
 // Number of the nph = nmax - nb phantom copies of row r that survive dropout (warp-cooperative; the copies occupy the key
 // slots nb .. nmax-1 of the padded row, the mask index convention of attention_v2.cu: idx = r * nmax + key slot).
 __device__ __forceinline__ int phantom_kept(unsigned long long seed, long long r, int nb, int nmax, unsigned int thresh, int lane) {
@@ -210,6 +241,14 @@ extern "C" int dost_xattn_kv_ext_split(const float* dext, const int32_t* batch, 
   const long long rows = N + B;
   xtc::kv_ext_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dext, batch, ptr, N, B, H, dkv, dbeta_rows);
   return check_launch("xattn_kv_ext_split");
+}
+
+extern "C" int dost_xattn_kv_pad_split(const float* dpad, int npad, int reps, const int32_t* batch, const int32_t* ptr, long long N, int B,
+                                       int H, float* dkv, float* dbeta_rows, dost_stream_t stream) {
+  DOST_REQUIRE(dpad && batch && ptr && dkv && dbeta_rows && N > 0 && B > 0 && H % 128 == 0 && npad > 0 && reps >= 1, "kv_pad_split: bad args");
+  const long long rows = N + B;
+  xtc::kv_pad_split_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dpad, npad, reps, batch, ptr, N, B, H, dkv, dbeta_rows);
+  return check_launch("xattn_kv_pad_split");
 }
 
 #define DOST_XTC_DISPATCH(KERNEL, ...)                                        \

@@ -1467,6 +1467,22 @@ class _CrossAttentionTC(torch.autograd.Function):
                         a_bstride=T * dsp.ld, c_bstride=T * H, b_rowoff=ptr_ext)
             # d(extended keys) = dS^T q + P^T dO, written at each crystal's rows of the extended plane
             # (sequences s and s + B write the same crystal's rows: one launch per repetition, accumulating in order)
+            dkv = torch.empty(N, H, dtype=torch.float32, device=dev)
+            dbrows = torch.empty(B, H, dtype=torch.float32, device=dev)
+            if not L.switch("DOST_NO_XATTN_PADDED_DK"):
+                # per SEQUENCE into a padded buffer: plain batched problems (TMA store, then a TMA reduction store for the
+                # second product) instead of ragged accumulating ones per repetition; the split kernel sums the repetitions
+                dpad = torch.empty(S * npad, H, dtype=torch.float32, device=dev)
+                gemm_planes(M=npad, N=H, K=T, a=[dsp], a_mode=L.MC, b=qp, b_mode=L.MC, out=dpad, batch=S, a_bstride=T * dsp.ld,
+                            b_bstride=T * qp.ld, c_bstride=npad * H)
+                gemm_planes(M=npad, N=H, K=T, a=[pp], a_mode=L.MC, b=dop, b_mode=L.MC, out=dpad, accumulate=True, batch=S,
+                            a_bstride=T * pp.ld, b_bstride=T * dop.ld, c_bstride=npad * H)
+                L.check(lib.dost_xattn_kv_pad_split(L.p(dpad), npad, reps, L.p(g.batch), L.p(g.ptr), N, B, H, L.p(dkv), L.p(dbrows),
+                                                    L.stream()), "xattn_kv_pad_split")
+                dph = colsum(dbrows)
+                d_q = colsum(dq.view(S, T * H)).view(T, H) if ctx.bcast_q else dq
+                d_resid = colsum(d_out.view(S, T * H)).view(T, H) if ctx.bcast_r else d_out
+                return d_q, dkv, dph, d_resid, None, None, None, None, None
             dext = torch.empty(N + B, H, dtype=torch.float32, device=dev)
             p1, n1 = g.ragged(1)
             for rep in range(reps):
@@ -1475,8 +1491,6 @@ class _CrossAttentionTC(torch.autograd.Function):
                             accumulate=rep > 0, batch=B, a_bstride=T * dsp.ld, b_bstride=T * qp.ld, c_rowoff=p1, c_rowlim=n1)
                 gemm_planes(M=npad, N=H, K=T, a=[_rows(pp, r0, r1)], a_mode=L.MC, b=_rows(dop, r0, r1), b_mode=L.MC, out=dext,
                             accumulate=True, batch=B, a_bstride=T * pp.ld, b_bstride=T * dop.ld, c_rowoff=p1, c_rowlim=n1)
-            dkv = torch.empty(N, H, dtype=torch.float32, device=dev)
-            dbrows = torch.empty(B, H, dtype=torch.float32, device=dev)
             L.check(lib.dost_xattn_kv_ext_split(L.p(dext), L.p(g.batch), L.p(g.ptr), N, B, H, L.p(dkv), L.p(dbrows), L.stream()),
                     "xattn_kv_ext_split")
             dph = colsum(dbrows)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 11
+#define DOST_ABI_VERSION 12
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -282,6 +282,10 @@ int dost_xattn_kv_ext_build(const float* y, const float* beta, const int32_t* ba
                             int H, void* hi, void* lo, long long ldp, dost_stream_t stream);
 int dost_xattn_kv_ext_split(const float* dext, const int32_t* batch, const int32_t* ptr, long long N, int B, int H, float* dkv,
                             float* dbeta_rows, dost_stream_t stream);
+/* the same adjoint from key gradients computed per sequence into a padded buffer dpad [reps*B][npad][H] (sequence s = rep*B + b
+ * attends to crystal b): dkv[r] = sum_rep dpad[rep*B + b][r - ptr[b]], dbeta_rows[b] = sum_rep dpad[rep*B + b][n_b] */
+int dost_xattn_kv_pad_split(const float* dpad, int npad, int reps, const int32_t* batch, const int32_t* ptr, long long N, int B, int H,
+                            float* dkv, float* dbeta_rows, dost_stream_t stream);
 /* drop_p > 0: attention dropout (multihead_attention.py:71) with the counter-based mask of dost_xattn_fwd (index =
  * row * Nmax + key slot; the Nmax - n_b phantom copies occupy the slots n_b .. Nmax-1 and survive individually): the planes
  * hold mask / (1 - p) * P, the phantom column (surviving copies) / (1 - p) * P_phantom; the backward regenerates the mask. */

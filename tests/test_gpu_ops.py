@@ -944,11 +944,20 @@ def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, 
             ops.gemm_planes(M=Mb, N=Nb, K=K, a=[qa], a_mode=L.KC, b=kb, b_mode=L.KC, b_rows=Nb, out=ob, residual=rsd, batch=nb_,
                             a_bstride=Mb * qa.ld, b_bstride=Nb * kb.ld, c_bstride=Mb * Nb, res_bstride=Mb * Nb)
             outs["batched"] = ob
+            # (6) accumulating fp32 stores (the second key-gradient GEMM of the attention backward): out += v, single and
+            # batched; the TMA variant is a reduction store (cp.reduce.async.bulk.tensor .add)
+            o6 = res.clone()
+            ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, out=o6, accumulate=True)
+            outs["acc"] = o6
+            ob2 = rsd.clone()
+            ops.gemm_planes(M=Mb, N=Nb, K=K, a=[qa], a_mode=L.KC, b=kb, b_mode=L.KC, b_rows=Nb, out=ob2, accumulate=True, batch=nb_,
+                            a_bstride=Mb * qa.ld, b_bstride=Nb * kb.ld, c_bstride=Mb * Nb)
+            outs["acc_batched"] = ob2
         torch.cuda.synchronize()
         return outs
 
     reg, tma = run(False), run(True)
-    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide", "batched"):
+    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide", "batched", "acc", "acc_batched"):
         if reg[k] is None:
             continue
         assert not torch.isnan(tma[k].float()).any(), k
