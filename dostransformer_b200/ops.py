@@ -598,6 +598,8 @@ class _FFNBlock(torch.autograd.Function):
         ctx.save_for_backward(y, stats, ln_w, ln_b, w1, w2, *_planes_save(h0p), *_planes_save(h1p))
         ctx.prec = _PRECISION
         ctx.shape = y_nd.shape
+        # y is the output of an attention op whose backward wants this block's input gradient as GEMM operand planes
+        ctx.emit_grad_planes = bool(getattr(y_nd, "_dost_attn_out", False))
         return out.view(y_nd.shape)
 
     @staticmethod
@@ -630,8 +632,11 @@ class _FFNBlock(torch.autograd.Function):
             gemm_planes(M=F, N=H, K=M, a=[dv1p], a_mode=L.MC, b=h0p, b_mode=L.MC, out=dw1, split_k=_split_for(F, H, M))
             dh0 = torch.empty(M, H, dtype=torch.float32, device=dev)
             gemm_planes(M=M, N=H, K=F, a=[dv1p], a_mode=L.KC, b=w1p, b_mode=L.MC, out=dh0)
-            dy, _, dg, db, _, _ = ln_bwd_planes(dh0, y, stats, ln_w, ln_b, dres=d_out)
-        return dy.view(ctx.shape), dg, db, dw1, db1, dw2, db2
+            dy, dyp, dg, db, _, _ = ln_bwd_planes(dh0, y, stats, ln_w, ln_b, dres=d_out, want_planes=ctx.emit_grad_planes)
+        dy = dy.view(ctx.shape)
+        if dyp is not None:      # read by the attention backward when this very tensor reaches it unmodified (single consumer)
+            dy._dost_planes, dy._dost_planes_version = dyp, dy._version
+        return dy, dg, db, dw1, db1, dw2, db2
 
 
 def ffn_block(y, ln_w, ln_b, w1, b1, w2, b2):
@@ -1358,6 +1363,16 @@ class _CrossAttention(torch.autograd.Function):
         return d_q, dkv, dph, d_resid, None, None, None, None
 
 
+def _grad_planes(d_out: torch.Tensor, rows: int, cols: int) -> Planes:
+    """Operand planes of an incoming gradient: those its producer attached (the FFN block's LayerNorm backward writes them in
+    the same pass, `_FFNBlock.backward`), if the tensor arrived unmodified; else one conversion pass."""
+    pl = getattr(d_out, "_dost_planes", None)
+    if (pl is not None and pl.rows == rows and pl.cols == cols and (pl.lo is not None) == _with_lo() and d_out.is_contiguous()
+            and getattr(d_out, "_dost_planes_version", -1) == d_out._version):
+        return pl
+    return split_planes(d_out.reshape(rows, cols))
+
+
 def fused_attention_ok(H: int, max_keys: int, drop_p: float) -> bool:
     """True when the single-kernel attention forward (csrc/attn_fused.cu: QK^T -> fp32 softmax -> PK with the scores in
     TMEM) covers this call: at most 256 keys per sequence, H in {64, 128, 192, 256}, no attention dropout (the dropout
@@ -1448,8 +1463,8 @@ class _CrossAttentionTC(torch.autograd.Function):
         with precision_value(ctx.prec):
             ptr_ext, n_ext = g.ragged(reps)
             qp, kvp, pp = Planes(qh, ql, S * T, H), Planes(kh, kl, N + B, H), Planes(ph, pl_, S * T, npad)
+            dop = _grad_planes(d_out, S * T, H)
             d_out = d_out.contiguous()
-            dop = split_planes(d_out.view(S * T, H))
             # dP = dO k^T
             dP = torch.empty(S * T, npad, dtype=torch.float32, device=dev)
             gemm_planes(M=T, N=npad, K=H, a=[dop], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=dP, batch=S,
@@ -1509,7 +1524,9 @@ def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: 
     if (tc_active(kv) and H % 128 == 0 and S % graph.B == 0 and graph.nmax_host is not None
             and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")
             and (q.dim() == 3 or S == graph.B)):
-        return _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q), S, drop_p, seed)
+        out = _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q), S, drop_p, seed)
+        out._dost_attn_out = True        # (its backward takes the incoming gradient as operand planes, see _grad_planes)
+        return out
     return _CrossAttention.apply(q, kv, phantom, resid, graph, S, drop_p, seed)
 
 
@@ -1610,8 +1627,8 @@ def _self_attention_backward_planes(ctx, d_out):
     scale = float(H) ** -0.5
     qp, kp = Planes(qh, ql, S * Lq, H), Planes(kh, kl, S * Lk, H)
     pdp = Planes(ph, pl_, S * Lq, Lk)
+    dop = _grad_planes(d_out, S * Lq, H)
     d_out = d_out.contiguous()
-    dop = split_planes(d_out.view(S * Lq, H))
     # dPd = dO k^T
     dpd = torch.empty(S, Lq, Lp, dtype=torch.float32, device=dev)
     gemm_planes(M=Lq, N=Lp, K=H, a=[dop], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=dpd.view(S * Lq, Lp), batch=S,
@@ -1653,7 +1670,10 @@ def _planes3(t: torch.Tensor) -> Optional[Planes]:
 
 
 def self_attention(q, k, resid, drop_p: float = 0.0, seed: int = 0):
-    return _SelfAttention.apply(q, k, resid, drop_p, seed)
+    out = _SelfAttention.apply(q, k, resid, drop_p, seed)
+    if tc_active(q) and q.shape[-1] % 8 == 0:
+        out._dost_attn_out = True
+    return out
 
 
 # =====================================================================================================
