@@ -11,7 +11,7 @@ for tool in ("memcheck", "racecheck", "initcheck_tma1", "initcheck_tma0"):
     if not os.path.isfile(path):
         continue
     txt = open(path, errors="replace").read().splitlines()
-    out.append(f"== compute-sanitizer --tool {tool.split('_')[0]}{' DOST_GEMM_TMA_EPI=' + tool[-1] if '_tma' in tool else ''}  (scripts/gpu_sanitize2.sh)")
+    out.append(f"== compute-sanitizer --tool {tool.split('_')[0]}{' DOST_GEMM_TMA_EPI=' + tool[-1] if '_tma' in tool else ''}  (scripts/gpu_sanitize.sh)")
     kinds = {}
     for i, ln in enumerate(txt):
         m = re.match(r"=+ (Invalid|Uninitialized|Race|Error|Program hit|Potential|Warning)[^\n]*", ln)
