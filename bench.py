@@ -245,6 +245,7 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
                 b1, b2 = torch.randn(F, device=dev), torch.randn(Hh, device=dev)
                 dop = ops.split_planes(torch.randn(M, Hh, device=dev))
                 dv1p = ops.empty_planes(M, F, dev, ops._with_lo())
+                gate = torch.zeros(F // 32, M, dtype=torch.int32, device=dev) if ops.gate_bits_ok(M, F) else None
                 o_mh, db1 = torch.empty(M, Hh, device=dev), torch.empty(F, device=dev)
                 dw2, dw1 = torch.empty(Hh, F, device=dev), torch.empty(F, Hh, device=dev)
                 sk2, sk1 = ops._split_for(Hh, F, M), ops._split_for(F, Hh, M)
@@ -255,13 +256,13 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
                         fn()
                 return run
             fns = [
-                ("fc1 fwd (bias+ReLU -> hi/lo planes)", M, F, Hh, wrap(lambda: ops.gemm_planes(
-                    M=M, N=F, K=Hh, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p))),
+                ("fc1 fwd (bias+ReLU -> hi/lo planes + gate bits)", M, F, Hh, wrap(lambda: ops.gemm_planes(
+                    M=M, N=F, K=Hh, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p, out_gate=gate))),
                 ("fc2 fwd (bias+residual -> fp32)", M, Hh, F, wrap(lambda: ops.gemm_planes(
                     M=M, N=Hh, K=F, a=[h1p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=y, out=o_mh))),
-                ("fc2 dA (relu' mask, planes out, bias-grad column sums)", M, F, Hh, wrap(lambda: ops.gemm_planes(
-                    M=M, N=F, K=Hh, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p, dact_slope=0.0, out_planes=dv1p,
-                    colsum_out=db1))),
+                ("fc2 dA (relu' gate bits, planes out, bias-grad column sums)", M, F, Hh, wrap(lambda: ops.gemm_planes(
+                    M=M, N=F, K=Hh, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p if gate is None else None, dact_gate=gate,
+                    dact_slope=0.0, out_planes=dv1p, colsum_out=db1))),
                 ("fc1 dA (fp32)", M, Hh, F, wrap(lambda: ops.gemm_planes(
                     M=M, N=Hh, K=F, a=[dv1p], a_mode=L.KC, b=w1p, b_mode=L.MC, out=o_mh))),
                 ("fc2 dW (split-K)", Hh, F, M, wrap(lambda: ops.gemm_planes(

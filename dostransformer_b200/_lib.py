@@ -22,7 +22,7 @@ PREC_FMA, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FMA, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 12
+ABI_VERSION = 13
 DEVERR_MESSAGES = {1: "an index (edge_index / batch / system) is outside its table",
                    2: "a crystal has more atoms than the padding length given by the host (max_num_nodes)"}
 
@@ -68,6 +68,7 @@ class GemmBf16(C.Structure):
         ("res_bstride", C.c_longlong),
         ("b_rowoff", C.c_void_p), ("c_rowoff", C.c_void_p), ("c_rowlim", C.c_void_p),
         ("colsum", C.c_void_p),
+        ("out_gate", C.c_void_p), ("dact_gate", C.c_void_p), ("ld_gate", C.c_longlong),
     ]
 
 

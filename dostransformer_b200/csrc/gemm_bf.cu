@@ -57,6 +57,10 @@ struct Params {
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; long long ld_op;
   float* ws;
   float* colpart;               // [ceil(M / 32)][N] per-32-row column sums of the stored value (bias gradients)
+  unsigned int* out_gate;       // [N / 32][ld_gate] words (word-major: a warp's 32 rows are 32 consecutive words): bit j of word
+                                // (w, m) = pre-activation value of element (m, 32 w + j) > 0 (written by the TMA-store epilogue)
+  const unsigned int* dact_gate;   // the same bits read back as the act' mask
+  long long ld_gate;
   int tma_epi;                  // epilogue variant: values finished in the accumulator's own layout (thread = row), staged in
                                 // the TMA-swizzled layout and written with cp.async.bulk.tensor stores (no second register pass)
 };
@@ -494,12 +498,12 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
     // round trips per chunk with only two epilogue warps per scheduler to hide them).  The empty asm statements keep the
     // compiler from rematerialising the loads.
     enum : uint32_t { F_BIAS = 1, F_ROWBIAS = 2, F_PRE = 4, F_ACT = 8, F_DACT = 16, F_RES = 32, F_OUT = 64, F_ACC = 128,
-                      F_HI = 256, F_LO = 512, F_COLPART = 1024, F_SPLITK = 2048, F_ROWLIM = 4096, F_TMA = 8192 };
+                      F_HI = 256, F_LO = 512, F_COLPART = 1024, F_SPLITK = 2048, F_ROWLIM = 4096, F_TMA = 8192, F_GATE_OUT = 16384, F_GATE_IN = 32768 };
     uint32_t feat = (p.bias ? F_BIAS : 0u) | (p.rowbias ? F_ROWBIAS : 0u) | (p.out_pre ? F_PRE : 0u) |
                     (p.act != DOST_ACT_NONE ? F_ACT : 0u) | (p.dact_hi ? F_DACT : 0u) | (p.residual ? F_RES : 0u) |
                     (p.out ? F_OUT : 0u) | (p.accumulate ? F_ACC : 0u) | (p.out_hi ? F_HI : 0u) | (p.out_lo ? F_LO : 0u) |
                     (p.colpart ? F_COLPART : 0u) | (p.zmode == 2 ? F_SPLITK : 0u) | (p.c_rowlim ? F_ROWLIM : 0u) |
-                    (p.tma_epi ? F_TMA : 0u);
+                    (p.tma_epi ? F_TMA : 0u) | (p.out_gate ? F_GATE_OUT : 0u) | (p.dact_gate ? F_GATE_IN : 0u);
     int Mv = p.M, Nv = p.N;
     long long ldc_v = p.ldc, ldop_v = p.ld_op, ldres_v = p.ld_res;
     const float* bias_v = p.bias;
@@ -532,7 +536,15 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
           for (int j = 0; j < CW / 8; ++j) pre[j] = ldg128u_nc_if(dp + 8 * j, ok && n0 + 8 * j < Nv);
         }
       };
+      // 1-bit gates: one word per row and 32 columns (16-column chunks: the word is shared by two consecutive chunks)
+      uint32_t gate_w = 0u;
+      auto prefetch_gate = [&](int c0n) {
+        const int n0 = t.n0 + half * CH + c0n;
+        gate_w = 0u;
+        if (mrow_t < Mv && n0 < Nv) gate_w = __ldg(p.dact_gate + (long long)(n0 >> 5) * p.ld_gate + mrow_t);
+      };
       if ((feat & F_TMA) && (feat & (F_RES | F_DACT))) prefetch_side(0);
+      if (feat & F_GATE_IN) prefetch_gate(0);
       mbar_wait(accf0 + 8 * buf, acc_phase[buf]);
       acc_phase[buf] ^= 1;
       tc_fence_after();
@@ -551,6 +563,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
         const int mrow = t.m0 + quad * 32 + lane;
         const bool row_ok = mrow < Mv;
         const bool warp_rows_ok = t.m0 + quad * 32 < Mv;
+        uint32_t gate_acc = 0u;
 #pragma unroll 1
         for (int c0 = 0; c0 < CH; c0 += CW) {
           const int n0 = t.n0 + half * CH + c0;            // first column of the chunk (warp-uniform)
@@ -586,9 +599,30 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
+          if (feat & F_GATE_OUT) {
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int j = 0; j < CW; ++j) bits |= (v[j] > 0.f ? 1u : 0u) << j;
+            if (CW == 32) {
+              if (row_ok) p.out_gate[(long long)(n0 >> 5) * p.ld_gate + mrow] = bits;
+            } else {                                        // two 16-column chunks per word
+              if (n0 & 16) {
+                if (row_ok) p.out_gate[(long long)(n0 >> 5) * p.ld_gate + mrow] = gate_acc | (bits << 16);
+              } else {
+                gate_acc = bits;
+              }
+            }
+          }
           if (feat & F_ACT) {
 #pragma unroll
             for (int j = 0; j < CW; ++j) v[j] = (v[j] > 0.f) ? v[j] : pslope * v[j];
+          }
+          if (feat & F_GATE_IN) {
+            const float ds = p.dact_slope;
+            const uint32_t gsh = gate_w >> (CW == 32 ? 0 : (n0 & 16));
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[j] = ((gsh >> j) & 1u) ? v[j] : ds * v[j];
+            if (c0 + CW < CH && (CW == 32 || (n0 & 16))) prefetch_gate(c0 + CW);
           }
           if (feat & F_DACT) {
             const float ds = p.dact_slope;
@@ -1334,6 +1368,10 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   p.residual = h->residual; p.ld_res = h->ld_res;
   p.out = h->out; p.ldc = h->ldc; p.accumulate = h->accumulate;
   p.out_hi = (__nv_bfloat16*)h->out_hi; p.out_lo = (__nv_bfloat16*)h->out_lo; p.ld_op = h->ld_op;
+  p.out_gate = h->out_gate; p.dact_gate = h->dact_gate; p.ld_gate = h->ld_gate;
+  DOST_REQUIRE(!(h->out_gate || h->dact_gate) || (h->N % 32 == 0 && h->ld_gate >= h->M && batch == 1 && split == 1 &&
+                                                  !(h->dact_gate && h->dact_hi)),
+               "gemm_bf16: activation gates need N %% 32 == 0, ld_gate >= M, a single un-split problem and no dact_hi");
   p.colpart = nullptr;
   const int nrb = (h->M + 31) / 32;
   if (h->colsum) {
@@ -1382,6 +1420,10 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
     else ew16 = false;
   }
 
+  if ((h->out_gate || h->dact_gate) && !p.tma_epi) {
+    set_error("gemm_bf16: activation gates are implemented by the TMA-store epilogue only (this launch is not eligible)");
+    return DOST_ERR_UNSUPPORTED;
+  }
   int rc;
   if (pairs && ew16) {
     rc = split3 ? launch<3, 256, true, 16>(maps, p, st) : launch<1, 256, true, 16>(maps, p, st);

@@ -447,9 +447,11 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
                 ldc: Optional[int] = None, prec: Optional[int] = None, batch: int = 1, a_bstride: int = 0, b_bstride: int = 0,
                 c_bstride: int = 0, res_bstride: int = 0, ld_res: Optional[int] = None, b_rows: Optional[int] = None,
                 b_rowoff: Optional[torch.Tensor] = None, c_rowoff: Optional[torch.Tensor] = None,
-                c_rowlim: Optional[torch.Tensor] = None, colsum_out: Optional[torch.Tensor] = None) -> None:
+                c_rowlim: Optional[torch.Tensor] = None, colsum_out: Optional[torch.Tensor] = None,
+                out_gate: Optional[torch.Tensor] = None, dact_gate: Optional[torch.Tensor] = None) -> None:
     """C = epi(A B^T) on the TMA-fed tcgen05 kernel; operands are bf16 planes (see include/dost.h).
-    b_rows: valid rows of a K-major B per problem when N is padded beyond them (the rest reads as zero)."""
+    b_rows: valid rows of a K-major B per problem when N is padded beyond them (the rest reads as zero).
+    out_gate / dact_gate: int32 [N / 32, M] activation gate bits written / read by the epilogue (see `gate_bits_ok`)."""
     g = L.GemmBf16()
     g.M, g.N, g.K = M, N, K
     g.a_mode, g.a_nseg = a_mode, len(a)
@@ -484,12 +486,22 @@ def gemm_planes(*, M: int, N: int, K: int, a: Sequence[Planes], a_mode: int, b: 
     g.split_k = split_k
     g.precision = _PRECISION if prec is None else prec
     g.colsum = colsum_out.data_ptr() if colsum_out is not None else None
+    if out_gate is not None:
+        g.out_gate, g.ld_gate = out_gate.data_ptr(), out_gate.stride(0)
+    if dact_gate is not None:
+        g.dact_gate, g.ld_gate, g.dact_slope = dact_gate.data_ptr(), dact_gate.stride(0), dact_slope
     lib = L.lib()
     ws, nb = None, 0
     if split_k > 1 or colsum_out is not None:
         nb = lib.dost_gemm_bf16_workspace_bytes(C.byref(g))
         ws = _ws(nb, b.hi.device)
     L.check(lib.dost_gemm_bf16(C.byref(g), L.p(ws), nb, L.stream()), "gemm_bf16")
+
+
+def gate_bits_ok(M: int, N: int) -> bool:
+    """The FFN keeps its ReLU gates as 1 bit per hidden activation (written by fc1's epilogue, read by the epilogue of the fc2
+    input-gradient GEMM instead of the 16-bit hi plane): needs the TMA-store epilogue (M >= 32, N % 32 == 0, not disabled)."""
+    return M >= 32 and N % 32 == 0 and os.environ.get("DOST_GEMM_TMA_EPI", "1") != "0" and not L.switch("DOST_NO_FFN_GATE")
 
 
 def tc_active(t: torch.Tensor) -> bool:
@@ -592,10 +604,11 @@ class _FFNBlock(torch.autograd.Function):
         _, h0p, stats = ln_fwd_planes(y, ln_w, ln_b)
         w1p, w2p = weight_planes(w1), weight_planes(w2)
         h1p = empty_planes(M, F, dev, _with_lo())
-        gemm_planes(M=M, N=F, K=H, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p)
+        gate = torch.empty(F // 32, M, dtype=torch.int32, device=dev) if gate_bits_ok(M, F) else None
+        gemm_planes(M=M, N=F, K=H, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p, out_gate=gate)
         out = torch.empty(M, H, dtype=torch.float32, device=dev)
         gemm_planes(M=M, N=H, K=F, a=[h1p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=y, out=out)
-        ctx.save_for_backward(y, stats, ln_w, ln_b, w1, w2, *_planes_save(h0p), *_planes_save(h1p))
+        ctx.save_for_backward(y, stats, ln_w, ln_b, w1, w2, *_planes_save(h0p), *_planes_save(h1p), gate)
         ctx.prec = _PRECISION
         ctx.shape = y_nd.shape
         # y is the output of an attention op whose backward wants this block's input gradient as GEMM operand planes
@@ -604,7 +617,7 @@ class _FFNBlock(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out_nd):
-        y, stats, ln_w, ln_b, w1, w2, h0h, h0l, h1h, h1l = ctx.saved_tensors
+        y, stats, ln_w, ln_b, w1, w2, h0h, h0l, h1h, h1l, gate = ctx.saved_tensors
         M, H = y.shape
         F = w1.shape[0]
         dev = y.device
@@ -626,8 +639,9 @@ class _FFNBlock(torch.autograd.Function):
             # d(relu input) = (d_out W2) * relu'(h1): relu' from the sign of the saved hi plane, result as planes only
             dv1p = empty_planes(M, F, dev, _with_lo())
             db1 = torch.empty(F, dtype=torch.float32, device=dev)      # bias gradient from the epilogue that writes dv1
-            gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p, dact_slope=0.0, out_planes=dv1p,
-                        colsum_out=db1)
+            # (the gates: 1 bit per element from fc1's epilogue when it wrote them, else the sign of the saved hi plane)
+            gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p if gate is None else None,
+                        dact_gate=gate, dact_slope=0.0, out_planes=dv1p, colsum_out=db1)
             dw1 = torch.empty(F, H, dtype=torch.float32, device=dev)
             gemm_planes(M=F, N=H, K=M, a=[dv1p], a_mode=L.MC, b=h0p, b_mode=L.MC, out=dw1, split_k=_split_for(F, H, M))
             dh0 = torch.empty(M, H, dtype=torch.float32, device=dev)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 12
+#define DOST_ABI_VERSION 13
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -168,6 +168,14 @@ typedef struct {
   /* optional: colsum[n] = sum_m (stored value)[m, n] in a fixed order, computed by the epilogue that stores it (the bias
    * gradient when the stored value is the gradient of a Linear's output); workspace ceil(M/32)*N floats; no split_k/batch */
   float* colsum;
+  /* optional 1-bit activation gates, [N / 32][ld_gate] 32-bit words (word-major, ld_gate >= M: the 32 rows of a warp are 32
+   * consecutive words), bit j of word (w, m) <-> element (m, 32 w + j); N % 32 == 0; plain single problems on the TMA-store
+   * epilogue only, else DOST_ERR_UNSUPPORTED.  out_gate: written by the epilogue, bit = (value after bias / row bias, before
+   * the activation) > 0.  dact_gate: read instead of dact_hi: v *= bit ? 1 : dact_slope.  (ReLU of layers/transformer.py:143:
+   * the backward then reads 1 bit instead of 16 per hidden activation.) */
+  uint32_t* out_gate;
+  const uint32_t* dact_gate;
+  long long ld_gate;
 } dost_gemm_bf16_t;
 
 size_t dost_gemm_bf16_workspace_bytes(const dost_gemm_bf16_t* g);

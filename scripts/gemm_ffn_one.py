@@ -23,11 +23,12 @@ with ops.precision(prec):
     dop = ops.split_planes(torch.randn(M, H, device=dev))
     dv1p = ops.split_planes(torch.randn(M, F, device=dev))
     o_mh, db1 = torch.empty(M, H, device=dev), torch.empty(F, device=dev)
+    gate = torch.zeros(F // 32, M, dtype=torch.int32, device=dev)
     dw2, dw1 = torch.empty(H, F, device=dev), torch.empty(F, H, device=dev)
     fns = {
-        "fc1_fwd": lambda: ops.gemm_planes(M=M, N=F, K=H, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p),
+        "fc1_fwd": lambda: ops.gemm_planes(M=M, N=F, K=H, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p, out_gate=gate),
         "fc2_fwd": lambda: ops.gemm_planes(M=M, N=H, K=F, a=[h1p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=y, out=o_mh),
-        "fc2_dA": lambda: ops.gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1p, dact_slope=0.0,
+        "fc2_dA": lambda: ops.gemm_planes(M=M, N=F, K=H, a=[dop], a_mode=L.KC, b=w2p, b_mode=L.MC, dact_gate=gate, dact_slope=0.0,
                                           out_planes=dv1p, colsum_out=db1),
         "fc1_dA": lambda: ops.gemm_planes(M=M, N=H, K=F, a=[dv1p], a_mode=L.KC, b=w1p, b_mode=L.MC, out=o_mh),
         "fc2_dW": lambda: ops.gemm_planes(M=H, N=F, K=M, a=[dop], a_mode=L.MC, b=h1p, b_mode=L.MC, out=dw2, split_k=ops._split_for(H, F, M)),

@@ -34,12 +34,14 @@ with ops.precision(prec):
     dop = [ops.split_planes(torch.randn(M, H, device=dev)) for _ in range(NBUF)]
     dv1 = [ops.split_planes(torch.randn(M, F, device=dev)) for _ in range(NBUF)]
     o_mh, db1 = torch.empty(M, H, device=dev), torch.empty(F, device=dev)
+    gates = [torch.zeros(F // 32, M, dtype=torch.int32, device=dev) for _ in range(NBUF)] if os.environ.get("GATES", "1") == "1" else None
     dw2, dw1 = torch.empty(H, F, device=dev), torch.empty(F, H, device=dev)
     fns = {
-        "fc1_fwd": lambda i: ops.gemm_planes(M=M, N=F, K=H, a=[h0[i]], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1[i]),
+        "fc1_fwd": lambda i: ops.gemm_planes(M=M, N=F, K=H, a=[h0[i]], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1[i],
+                                             out_gate=gates[i] if gates else None),
         "fc2_fwd": lambda i: ops.gemm_planes(M=M, N=H, K=F, a=[h1[i]], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=ys[i], out=o_mh),
-        "fc2_dA": lambda i: ops.gemm_planes(M=M, N=F, K=H, a=[dop[i]], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=h1[i], dact_slope=0.0,
-                                            out_planes=dv1[i], colsum_out=db1),
+        "fc2_dA": lambda i: ops.gemm_planes(M=M, N=F, K=H, a=[dop[i]], a_mode=L.KC, b=w2p, b_mode=L.MC, dact=None if gates else h1[i],
+                                            dact_gate=gates[i] if gates else None, dact_slope=0.0, out_planes=dv1[i], colsum_out=db1),
         "fc1_dA": lambda i: ops.gemm_planes(M=M, N=H, K=F, a=[dv1[i]], a_mode=L.KC, b=w1p, b_mode=L.MC, out=o_mh),
         "fc2_dW": lambda i: ops.gemm_planes(M=H, N=F, K=M, a=[dop[i]], a_mode=L.MC, b=h1[i], b_mode=L.MC, out=dw2, split_k=ops._split_for(H, F, M)),
         "fc1_dW": lambda i: ops.gemm_planes(M=F, N=H, K=M, a=[dv1[i]], a_mode=L.MC, b=h0[i], b_mode=L.MC, out=dw1, split_k=ops._split_for(F, H, M)),

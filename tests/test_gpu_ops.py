@@ -1089,3 +1089,40 @@ def test_fused_attention_ragged(prec, tol, H, broadcast, T, reps, sizes, monkeyp
         assert relerr(a_, b_) < (3e-5 if prec == "bf16x3" else 3e-2), (nm, relerr(a_, b_))
     torch.cuda.synchronize()
     L.poll_device_errors()
+
+
+@pytest.mark.parametrize("epi16", ["1", "0"])
+@pytest.mark.parametrize("prec", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 256), (300, 1024, 64), (100, 64, 64), (4100, 96, 128)])
+def test_planes_gemm_activation_gate_bits(prec, M, N, K, epi16, monkeypatch):
+    """1-bit activation gates of the GEMM epilogue (the FFN's ReLU, layers/transformer.py:143): out_gate holds
+    (pre-activation > 0) for every element, bit-exact against the fp32 pre-activations of the same kernel; reading them back
+    as the act' mask gives bit for bit the result of the 16-bit sign-plane mask.  8-warp / 32-column and 16-warp /
+    16-column epilogues, ragged M tails."""
+    monkeypatch.setenv("DOST_GEMM_EPI16", epi16)
+    torch.manual_seed(M + N + K)
+    a, w, bias = torch.randn(M, K, device=DEV), torch.randn(N, K, device=DEV), torch.randn(N, device=DEV)
+    g2 = torch.randn(M, 64, device=DEV)
+    w2 = torch.randn(N, 64, device=DEV)
+    with ops.precision(prec):
+        assert ops.gate_bits_ok(M, N)
+        lo = prec != "bf16"
+        ap, wp = ops.split_planes(a), ops.split_planes(w)
+        pre = torch.empty(M, N, device=DEV)
+        ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=L.KC, bias=bias, out=pre)
+        hp = ops.empty_planes(M, N, DEV, with_lo=lo)
+        gate = torch.full((N // 32, M), -1, dtype=torch.int32, device=DEV)
+        ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=L.KC, bias=bias, act=L.ACT_RELU, out_planes=hp, out_gate=gate)
+        bits = ((gate.t().reshape(M, N // 32, 1) >> torch.arange(32, device=DEV, dtype=torch.int32)) & 1).reshape(M, N).bool()
+        assert torch.equal(bits, pre > 0)
+        # the mask read back: (g2 w2^T) * relu'(.) with the gates vs with the sign of the saved hi plane
+        gp, w2p = ops.split_planes(g2), ops.split_planes(w2)
+        o_bits, o_plane = ops.empty_planes(M, N, DEV, with_lo=lo), ops.empty_planes(M, N, DEV, with_lo=lo)
+        cs_bits, cs_plane = torch.empty(N, device=DEV), torch.empty(N, device=DEV)
+        ops.gemm_planes(M=M, N=N, K=64, a=[gp], a_mode=L.KC, b=w2p, b_mode=L.KC, dact_gate=gate, dact_slope=0.0, out_planes=o_bits,
+                        colsum_out=cs_bits)
+        ops.gemm_planes(M=M, N=N, K=64, a=[gp], a_mode=L.KC, b=w2p, b_mode=L.KC, dact=hp, dact_slope=0.0, out_planes=o_plane,
+                        colsum_out=cs_plane)
+        # (a positive pre-activation below the smallest bf16 would flush the plane's sign but not the bit: not in this data)
+        assert torch.equal(o_bits.hi, o_plane.hi) and (not lo or torch.equal(o_bits.lo, o_plane.lo))
+        assert torch.equal(cs_bits, cs_plane)
