@@ -52,14 +52,27 @@ __global__ void __launch_bounds__(kWarps * 32) ln_fwd_kernel(float* __restrict__
   const bool has_act = slope_p != nullptr;
   const float slope = has_act ? __ldg(slope_p) : 0.f;
   const float invW = 1.f / W;
-  for (long long r = blockIdx.x * (long long)kWarps + warp; r < M; r += (long long)gridDim.x * kWarps) {
+  // gather indices of this warp's NEXT row are requested one iteration ahead: the gathers then depend on a value that is
+  // already there instead of adding an index round trip to every row's latency chain
+  const long long rstep = (long long)gridDim.x * kWarps;
+  long long r = blockIdx.x * (long long)kWarps + warp;
+  long long ra_n = 0, rb_n = 0;
+  if (ga && r < M) {
+    ra_n = __ldg(ia + r);
+    rb_n = __ldg(ib + r);
+  }
+  for (; r < M; r += rstep) {
     float4 v[NV];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i)
       v[i] = *(reinterpret_cast<const float4*>(x + r * ldx) + lane + 32 * i);
     if (ga) {
-      const long long ra = __ldg(ia + r), rb = __ldg(ib + r);
+      const long long ra = ra_n, rb = rb_n;
+      if (r + rstep < M) {
+        ra_n = __ldg(ia + r + rstep);
+        rb_n = __ldg(ib + r + rstep);
+      }
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(ga + ra * ldg) + lane + 32 * i);

@@ -127,7 +127,17 @@ class CrystalGraph:
     crystals: CSR        # nodes grouped by crystal (contiguous): ptr = crystals.rowptr
     nmax: torch.Tensor   # int32 [1] on device: max nodes per crystal (to_dense_batch padding length)
     nmax_host: Optional[int] = None   # the same number on the host when the collate / sharder knows it (no device sync)
+    # this batch's OWN largest crystal (<= nmax_host, which may be the data-parallel global padding length): sizes the
+    # attention's key-side buffers, so that a rank's work does not grow with the other ranks' crystals; the phantom-key
+    # multiplicity always uses `nmax`
+    nmax_local: Optional[int] = None
     _trows: dict = field(default_factory=dict)
+
+    @property
+    def nkeys_host(self) -> Optional[int]:
+        """Host-side bound on the keys of one sequence: the crystal's atoms + the phantom column."""
+        n = self.nmax_local if self.nmax_local is not None else self.nmax_host
+        return None if n is None else n + 1
 
     def ragged(self, reps: int = 1):
         """(ptr_ext, n_ext): first row and row count of every crystal in the extended key plane (atoms + 1 phantom row),
@@ -203,7 +213,8 @@ def build_graph(edge_index: torch.Tensor, batch: torch.Tensor, system: torch.Ten
         # reference reads back twice per forward: len(batch.unique()) DOSTransformer.py:118 and to_dense_batch's max().)
         # Batches from this package's collate / sharder / synthetic generators carry the hint and never get here.
         host = int(nmax.item())
-    return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host)
+    local = int(nmax_hint) if (nmax_hint is not None and host is not None) else host
+    return CrystalGraph(N, E, B, row, col, b32, s32, by_dst, by_src, by_sys, crystals, nmax, host, local)
 
 
 # =====================================================================================================
@@ -1424,7 +1435,7 @@ class _CrossAttentionTC(torch.autograd.Function):
         reps = S // B
         dev = kv.device
         lib = L.lib()
-        npad = _pad8(graph.nmax_host + 1)
+        npad = _pad8(graph.nkeys_host)
         ptr_ext, n_ext = graph.ragged(reps)
         q, resid = q.contiguous(), resid.contiguous()
         bcast_q = q.dim() == 2
@@ -1441,11 +1452,11 @@ class _CrossAttentionTC(torch.autograd.Function):
         ctx.graph, ctx.prec, ctx.npad = graph, _PRECISION, npad
         ctx.bcast_q, ctx.bcast_r, ctx.T, ctx.S = bcast_q, resid.dim() == 2, T, S
         ctx.drop_p, ctx.seed = drop_p, seed
-        ctx.fused = fused_attention_ok(H, graph.nmax_host + 1, drop_p)
+        ctx.fused = fused_attention_ok(H, graph.nkeys_host, drop_p)
         if ctx.fused:
             # one kernel: scores stay in TMEM, the probabilities leave only as the operand planes the backward needs
             pp = empty_planes(S * T, npad, dev, _with_lo()) if any(ctx.needs_input_grad[:4]) else None
-            _fused_attention_fwd(qp, kvp, N + B, S, T, 0, H, ptr_ext, n_ext, graph.nmax, graph.nmax_host + 1, r2,
+            _fused_attention_fwd(qp, kvp, N + B, S, T, 0, H, ptr_ext, n_ext, graph.nmax, graph.nkeys_host, r2,
                                  0 if resid.dim() == 2 else T * H, out.view(S * T, H), pp)
             if pp is not None:
                 ctx.save_for_backward(kv, phantom, None, None, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
@@ -1536,7 +1547,7 @@ def _rows(pl: Planes, r0: int, r1: int) -> Planes:
 def cross_attention(q, kv, phantom, resid, graph: CrystalGraph, S: int, drop_p: float = 0.0, seed: int = 0):
     H = kv.shape[1]
     if (tc_active(kv) and H % 128 == 0 and S % graph.B == 0 and graph.nmax_host is not None
-            and graph.nmax_host + 1 <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")
+            and graph.nkeys_host <= 1016 and q.shape[-2] >= 64 and not L.switch("DOST_NO_XATTN_TC")
             and (q.dim() == 3 or S == graph.B)):
         out = _CrossAttentionTC.apply(q, kv, phantom, resid, graph, _planes3(q), S, drop_p, seed)
         out._dost_attn_out = True        # (its backward takes the incoming gradient as operand planes, see _grad_planes)
