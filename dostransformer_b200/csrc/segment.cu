@@ -33,42 +33,39 @@ __global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_vec_kernel(
     Vec acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = Acc<T>::zero();
-    int j = beg;
-    for (; j + 4 <= end; j += 4) {
-      long long r0, r1, r2, r3;
-      if (perm) {
-        r0 = __ldg(perm + j); r1 = __ldg(perm + j + 1); r2 = __ldg(perm + j + 2); r3 = __ldg(perm + j + 3);
-      } else {
-        r0 = j; r1 = j + 1; r2 = j + 2; r3 = j + 3;
-      }
-      Vec v0[NV], v1[NV], v2[NV], v3[NV];
+    // The row indices of (up to) 32 edges are fetched by ONE coalesced load and handed out by shuffles: the row loads of a
+    // group then depend on a single index round trip instead of one per 4 rows, and up to RB rows are in flight per lane.
+    // The sum runs over the edges in ascending CSR order (fixed order, same as before).
+    constexpr int RB = NV <= 2 ? 8 : (NV <= 4 ? 4 : 2);
+    for (int base = beg; base < end; base += 32) {
+      const int n = min(32, end - base);
+      int myrow = base + lane;
+      if (perm && lane < n) myrow = __ldg(perm + base + lane);
+      int j = 0;
+      for (; j + RB <= n; j += RB) {
+        Vec v[RB][NV];
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        if (c < nvec) {
-          v0[i] = __ldg(reinterpret_cast<const Vec*>(src + r0 * ld) + c);
-          v1[i] = __ldg(reinterpret_cast<const Vec*>(src + r1 * ld) + c);
-          v2[i] = __ldg(reinterpret_cast<const Vec*>(src + r2 * ld) + c);
-          v3[i] = __ldg(reinterpret_cast<const Vec*>(src + r3 * ld) + c);
+        for (int k = 0; k < RB; ++k) {
+          const long long r = __shfl_sync(0xffffffffu, myrow, j + k);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nvec) v[k][i] = __ldg(reinterpret_cast<const Vec*>(src + r * ld) + c);
+          }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        if (c < nvec) {
-          Acc<T>::add(acc[i], v0[i]);
-          Acc<T>::add(acc[i], v1[i]);
-          Acc<T>::add(acc[i], v2[i]);
-          Acc<T>::add(acc[i], v3[i]);
+        for (int k = 0; k < RB; ++k)
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+            if (lane + 32 * i < nvec) Acc<T>::add(acc[i], v[k][i]);
+      }
+      for (; j < n; ++j) {
+        const long long r = __shfl_sync(0xffffffffu, myrow, j);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int c = lane + 32 * i;
+          if (c < nvec) Acc<T>::add(acc[i], __ldg(reinterpret_cast<const Vec*>(src + r * ld) + c));
         }
-      }
-    }
-    for (; j < end; ++j) {
-      const long long r = perm ? (long long)__ldg(perm + j) : (long long)j;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        const int c = lane + 32 * i;
-        if (c < nvec) Acc<T>::add(acc[i], __ldg(reinterpret_cast<const Vec*>(src + r * ld) + c));
       }
     }
     const int cnt = end - beg;
