@@ -89,6 +89,68 @@ __global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_vec_kernel(
   }
 }
 
+// Few segments (per-crystal reductions: the adjoint of a broadcast over the T energy tokens, crystal pooling): one BLOCK per
+// segment instead of one warp - a warp walking 201 rows serially took 56-65 us at any batch size.  Warp w sums rows
+// beg + w, beg + w + 8, ... in ascending order, then the 8 partial sums are added in warp order: a fixed order.
+template <typename T, int NV>
+__global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_block_kernel(
+    const T* __restrict__ src, long long ld, const int* __restrict__ rowptr, const int* __restrict__ perm,
+    long long nseg, int W, int mean, int accumulate, T* __restrict__ out, long long ldo) {
+  constexpr int V = VecOf<T>::N;
+  using Vec = typename VecOf<T>::type;
+  __shared__ Vec part[kSegWarps][NV * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nvec = W / V;
+  for (long long s = blockIdx.x; s < nseg; s += gridDim.x) {
+    const int beg = __ldg(rowptr + s), end = __ldg(rowptr + s + 1);
+    Vec acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) acc[i] = Acc<T>::zero();
+    int j = beg + warp;
+    for (; j + 3 * kSegWarps < end; j += 4 * kSegWarps) {     // four rows in flight per lane
+      long long r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = perm ? (long long)__ldg(perm + j + k * kSegWarps) : (long long)(j + k * kSegWarps);
+      Vec v[4][NV];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (lane + 32 * i < nvec) v[k][i] = __ldg(reinterpret_cast<const Vec*>(src + r[k] * ld) + lane + 32 * i);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          if (lane + 32 * i < nvec) Acc<T>::add(acc[i], v[k][i]);
+    }
+    for (; j < end; j += kSegWarps) {
+      const long long r = perm ? (long long)__ldg(perm + j) : (long long)j;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (lane + 32 * i < nvec) Acc<T>::add(acc[i], __ldg(reinterpret_cast<const Vec*>(src + r * ld) + lane + 32 * i));
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) part[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    const int cnt = end - beg;
+    const T sc = (mean && cnt > 1) ? T(1) / T(cnt) : T(1);
+    for (int c = threadIdx.x; c < nvec; c += kSegWarps * 32) {
+      Vec v = part[0][c];
+#pragma unroll
+      for (int w = 1; w < kSegWarps; ++w) Acc<T>::add(v, part[w][c]);
+      if (mean) Acc<T>::scale(v, sc);
+      Vec* op = reinterpret_cast<Vec*>(out + s * ldo) + c;
+      if (accumulate) {
+        Vec o = *op;
+        Acc<T>::add(o, v);
+        v = o;
+      }
+      *op = v;
+    }
+    __syncthreads();
+  }
+}
+
 // scalar fallback for unaligned / odd widths
 template <typename T>
 __global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_scalar_kernel(
@@ -188,6 +250,18 @@ static int run_segment_reduce(const void* src, long long ld, const int* rowptr, 
   constexpr int V = VecOf<T>::N;
   int blocks = (int)min64((nseg + kSegWarps - 1) / kSegWarps, 32LL * kNumSMs);
   const bool vec = (W % V == 0) && (ld % V == 0) && (ldo % V == 0) && al16(src) && al16(out) && W <= 32 * V * 8;
+  if (vec && nseg <= 1024 && W <= 32 * V * 4) {      // few segments: a block per segment (see segment_reduce_block_kernel)
+    const int nv = (W / V + 31) / 32;
+    const int nb = (int)nseg;
+#define DOST_SEGB(NV)                                                                                                    \
+  segment_reduce_block_kernel<T, NV><<<nb, kSegWarps * 32, 0, st>>>((const T*)src, ld, rowptr, perm, nseg, W, mean, accumulate, \
+                                                                    (T*)out, ldo)
+    if (nv <= 1) DOST_SEGB(1);
+    else if (nv <= 2) DOST_SEGB(2);
+    else DOST_SEGB(4);
+#undef DOST_SEGB
+    return check_launch("segment_reduce");
+  }
   if (vec) {
     const int nv = (W / V + 31) / 32;
 #define DOST_SEG(NV)                                                                                              \

@@ -278,8 +278,18 @@ def gemm_raw(*, M: int, N: int, K: int, a: Sequence[Tuple[torch.Tensor, Optional
     g.ldc = ldc if ldc is not None else _ld(out if out.dim() == 2 else out.reshape(-1, out.shape[-1]))
     g.c_bstride = c_bstride
     g.accumulate = 1 if accumulate else 0
+    precision = _PRECISION if prec is None else prec
+    # Small fp32 problems (the per-crystal Linears of the DOS heads: [B, 2H] x [2H, H] and their adjoints) are latency-bound:
+    # a few tiles whose K loop runs serially - 44 us on the converting tensor-core kernel at ANY batch size.  They go to the
+    # FMA pipe (exact fp32) with the reduction split over up to 8 blocks when the epilogue is a plain store.
+    if (precision != L.PREC_FMA and out.dtype == torch.float32 and batch == 1 and M * N * K < (1 << 27)
+            and not L.switch("DOST_NO_SMALL_FMA")):
+        precision = L.PREC_FMA
+        if (split_k == 1 and K >= 256 and bias is None and act == L.ACT_NONE and out_pre is None and dact_saved is None
+                and residual is None):
+            split_k = min(8, K // 64)
     g.split_k = split_k
-    g.precision = _PRECISION if prec is None else prec
+    g.precision = precision
     lib = L.lib()
     ws, nb = None, 0
     if split_k > 1:

@@ -239,8 +239,9 @@ def test_layer_norm(dtype, W, prelu):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 @pytest.mark.parametrize("mean", [False, True])
-def test_segment_reduce(dtype, mean):
-    E, N, W = 4000, 300, 256
+@pytest.mark.parametrize("E,N", [(4000, 300), (30000, 2500)])     # block-per-segment kernel (<= 1024 segments) / warp-per-segment
+def test_segment_reduce(dtype, mean, E, N):
+    W = 256
     src = _leaf(_rand(E, W, dtype=dtype, seed=1))
     key = torch.randint(0, N - 5, (E,), generator=torch.Generator().manual_seed(3))
     key[:600] = 7                                                    # hub
@@ -256,6 +257,14 @@ def test_segment_reduce(dtype, mean):
     src2 = _rand(E, 41, dtype=dtype, seed=2)
     out2 = ops.segment_reduce_raw(src2[:, 3:40], csr.rowptr, csr.perm, N)
     assert relerr(out2, O.segment_sum(src2[:, 3:40], kd, N)) < TOL[dtype] * 20
+    # contiguous groups (no permutation), accumulating into an existing tensor: the adjoint of a per-crystal broadcast
+    G, Tn = (N // 10), 201
+    src3 = _rand(G * Tn, W, dtype=dtype, seed=4)
+    rp = (torch.arange(G + 1, dtype=torch.int32, device=DEV) * Tn).contiguous()
+    acc = _rand(G, W, dtype=dtype, seed=5)
+    want = acc.double() + src3.double().view(G, Tn, W).sum(1)
+    ops.segment_reduce_raw(src3, rp, None, G, out=acc, accumulate=True)
+    assert relerr(acc, want) < TOL[dtype] * 20
 
 
 def _dense_cross_ref(q, x_nodes, gam, bet, batch, H):
