@@ -22,7 +22,7 @@ PREC_FMA, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FMA, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 13
+ABI_VERSION = 14
 DEVERR_MESSAGES = {1: "an index (edge_index / batch / system) is outside its table",
                    2: "a crystal has more atoms than the padding length given by the host (max_num_nodes)"}
 
@@ -158,7 +158,7 @@ _SIGNATURES = {
     "dost_attn_fused_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong,
                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
                                       C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int,
-                                      C.c_void_p]),
+                                      C.c_double, C.c_ulonglong, C.c_void_p, C.c_void_p]),
     "dost_softmax_bwd_from_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int,
                                                C.c_double, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dost_eval_metrics": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -66,6 +66,13 @@ struct Params {
   float* out;
   int store_p;
   unsigned int* errw;
+  // attention dropout (multihead_attention.py:71): counter-based keep mask of the library (common.cuh), index =
+  // row * mask_ld + key slot with mask_ld = Lk (dense) or the padding length Nmax (ragged: the phantom copies occupy the slots
+  // n_b .. Nmax-1 and survive individually); thresh == 0: off
+  unsigned int thresh;
+  float inv_keep;
+  unsigned long long seed;
+  float* lse;                    // optional [S * Lq]: log-sum-exp of the scaled scores (the dropout backward recomputes P)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -463,10 +470,32 @@ __global__ void __launch_bounds__(kThreads, 1) attn_fwd_kernel(const __grid_cons
       // ---- pass 3: p = e / sum as bf16 hi/lo, K-major SWIZZLE_128B tile [128 rows][64-key blocks] over the dead Q tile
       const uint32_t prow = sQP + row * 128;
       const uint32_t swz = row & 7;
+      // dropout: this row's mask indices start at rglob * mask_ld; the phantom column keeps (surviving copies) / nph of its mass
+      const unsigned int thresh = p.thresh;
+      const long long rglob = (long long)it.s * p.Lq + it.m0 + row;
+      const int mask_ld = p.k_rowoff ? (p.nmax ? __ldg(p.nmax) : p.kpad) : p.Lk;
+      const unsigned long long mbase = (unsigned long long)rglob * (unsigned long long)mask_ld;
+      float ph_scale = 1.f;
+      if (thresh && it.nph > 0 && it.nb >= cbeg * KC && it.nb < cend * KC) {
+        int kept = 0;
+        for (int jj = it.nb; jj < it.nb + it.nph; ++jj) kept += keep_mask(p.seed, mbase + jj, thresh) ? 1 : 0;
+        ph_scale = (float)kept * p.inv_keep / (float)it.nph;
+      }
+      if (p.lse && half == 0 && it.m0 + row < p.Lq) p.lse[rglob] = mx * 0.6931471805599453f + logf(xsum[row] + xsum[BM + row]);
       for (int c = cbeg; c < cend; ++c) {
         tmem_ld32(tmem_S + lane_addr + c * KC, r);
         tmem_ld_wait();
         const uint32_t pb = prow + (c >> 1) * 16384;
+        if (thresh) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = c * KC + j;
+            float e = __uint_as_float(r[j]);
+            if (col == it.nb) e *= ph_scale;
+            else e = keep_mask(p.seed, mbase + col, thresh) ? e * p.inv_keep : 0.f;
+            r[j] = __float_as_uint(e);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint32_t hi[4], lo[4];
@@ -672,7 +701,8 @@ extern "C" int dost_attn_fused_supported(int Lq, int H, int max_keys) {
 extern "C" int dost_attn_fused_fwd(const void* q_hi, const void* q_lo, long long ld_q, const void* k_hi, const void* k_lo, long long ld_k,
                                    long long k_rows, int S, int Lq, int Lk, int H, const int32_t* k_rowoff, const int32_t* k_count,
                                    const int32_t* nmax, int max_keys, double scale, const float* residual, long long res_seq_stride,
-                                   float* out, void* p_hi, void* p_lo, long long ld_p, int precision, dost_stream_t stream) {
+                                   float* out, void* p_hi, void* p_lo, long long ld_p, int precision, double drop_p,
+                                   unsigned long long seed, float* lse, dost_stream_t stream) {
   DOST_REQUIRE(q_hi && k_hi && out && S > 0 && Lq > 0, "attn_fused_fwd: null pointer / empty problem");
   DOST_REQUIRE(precision == DOST_PREC_BF16X3 || precision == DOST_PREC_BF16, "attn_fused_fwd: precision must be bf16x3 or bf16");
   const bool split3 = precision == DOST_PREC_BF16X3;
@@ -701,6 +731,12 @@ extern "C" int dost_attn_fused_fwd(const void* q_hi, const void* q_lo, long long
   p.out = out;
   p.store_p = p_hi ? 1 : 0;
   p.errw = device_error_words();
+  DOST_REQUIRE(drop_p >= 0.0 && drop_p < 1.0, "attn_fused_fwd: drop_p must be in [0, 1)");
+  DOST_REQUIRE(!(drop_p > 0.0 && ragged && !nmax), "attn_fused_fwd: ragged dropout needs the device padding length");
+  p.thresh = drop_p > 0.0 ? drop_threshold(drop_p) : 0u;
+  p.inv_keep = (float)(1.0 / (1.0 - drop_p));
+  p.seed = seed;
+  p.lse = lse;
   int rc = fa::make_map(&maps.q_hi, q_hi, H, Lq, ld_q, fa::BM, S, (long long)Lq * ld_q);
   if (rc == DOST_OK && split3) rc = fa::make_map(&maps.q_lo, q_lo, H, Lq, ld_q, fa::BM, S, (long long)Lq * ld_q);
   auto kmap = [&](CUtensorMap* m, const void* base, int box_rows) {

@@ -1408,21 +1408,21 @@ def _grad_planes(d_out: torch.Tensor, rows: int, cols: int) -> Planes:
     return split_planes(d_out.reshape(rows, cols))
 
 
-def fused_attention_ok(H: int, max_keys: int, drop_p: float) -> bool:
+def fused_attention_ok(H: int, max_keys: int, drop_p: float = 0.0) -> bool:
     """True when the single-kernel attention forward (csrc/attn_fused.cu: QK^T -> fp32 softmax -> PK with the scores in
-    TMEM) covers this call: at most 256 keys per sequence, H in {64, 128, 192, 256}, no attention dropout (the dropout
-    path keeps the GEMM + softmax + GEMM formulation).  DOST_NO_ATTN_FUSED=1 switches it off."""
-    return (drop_p == 0 and H % 64 == 0 and 64 <= H <= 256 and 1 <= max_keys <= 256 and _PRECISION != L.PREC_FMA
+    TMEM) covers this call: at most 256 keys per sequence, H in {64, 128, 192, 256}.  Attention dropout is applied inside
+    the kernel (same counter-based mask as the unfused kernels).  DOST_NO_ATTN_FUSED=1 switches it off."""
+    return (H % 64 == 0 and 64 <= H <= 256 and 1 <= max_keys <= 256 and _PRECISION != L.PREC_FMA
             and not L.switch("DOST_NO_ATTN_FUSED"))
 
 
 def _fused_attention_fwd(qp: Planes, kp: Planes, k_rows: int, S: int, Lq: int, Lk: int, H: int, rowoff, count, nmax, max_keys: int,
-                         resid2d, res_seq_stride: int, out2d, pp: Optional[Planes]):
+                         resid2d, res_seq_stride: int, out2d, pp: Optional[Planes], drop_p: float = 0.0, seed: int = 0, lse=None):
     L.check(L.lib().dost_attn_fused_fwd(L.p(qp.hi), L.p(qp.lo), qp.ld, L.p(kp.hi), L.p(kp.lo), kp.ld, k_rows, S, Lq, Lk, H,
                                         L.p(rowoff), L.p(count), L.p(nmax), max_keys, float(H) ** -0.5, L.p(resid2d),
                                         res_seq_stride, L.p(out2d), L.p(pp.hi) if pp is not None else None,
                                         L.p(pp.lo) if pp is not None else None, pp.ld if pp is not None else 0, _PRECISION,
-                                        L.stream()), "attn_fused_fwd")
+                                        float(drop_p), int(seed), L.p(lse), L.stream()), "attn_fused_fwd")
 
 
 def _ds_from_planes(pp: Planes, dP2d: torch.Tensor, rows: int, cols: int, scale: float, dsp: Planes):
@@ -1465,11 +1465,14 @@ class _CrossAttentionTC(torch.autograd.Function):
         ctx.fused = fused_attention_ok(H, graph.nkeys_host, drop_p)
         if ctx.fused:
             # one kernel: scores stay in TMEM, the probabilities leave only as the operand planes the backward needs
-            pp = empty_planes(S * T, npad, dev, _with_lo()) if any(ctx.needs_input_grad[:4]) else None
+            need = any(ctx.needs_input_grad[:4])
+            pp = empty_planes(S * T, npad, dev, _with_lo()) if need else None
+            # with dropout the planes hold the dropped-out probabilities; the backward recomputes P from the log-sum-exp
+            lse = torch.empty(S * T, dtype=torch.float32, device=dev) if (need and drop_p > 0) else None
             _fused_attention_fwd(qp, kvp, N + B, S, T, 0, H, ptr_ext, n_ext, graph.nmax, graph.nkeys_host, r2,
-                                 0 if resid.dim() == 2 else T * H, out.view(S * T, H), pp)
-            if pp is not None:
-                ctx.save_for_backward(kv, phantom, None, None, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
+                                 0 if resid.dim() == 2 else T * H, out.view(S * T, H), pp, drop_p, seed, lse)
+            if need:
+                ctx.save_for_backward(kv, phantom, None, lse, *_planes_save(qp), *_planes_save(kvp), *_planes_save(pp))
             return out
         scores = torch.empty(S * T, npad, dtype=torch.float32, device=dev)
         gemm_planes(M=T, N=npad, K=H, a=[qp], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=scores, batch=S,
@@ -1505,7 +1508,11 @@ class _CrossAttentionTC(torch.autograd.Function):
             gemm_planes(M=T, N=npad, K=H, a=[dop], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=dP, batch=S,
                         a_bstride=T * dop.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
             dsp = empty_planes(S * T, npad, dev, _with_lo())
-            if ctx.fused:      # probabilities from their saved planes (the phantom column behaves like one key of its total mass)
+            if ctx.fused and ctx.drop_p > 0:      # the scores once more (one ragged GEMM), then the softmax backward below
+                scores = torch.empty(S * T, npad, dtype=torch.float32, device=dev)
+                gemm_planes(M=T, N=npad, K=H, a=[qp], a_mode=L.KC, b=kvp, b_mode=L.KC, b_rows=N + B, out=scores, batch=S,
+                            a_bstride=T * qp.ld, c_bstride=T * npad, b_rowoff=ptr_ext)
+            if ctx.fused and ctx.drop_p == 0:      # probabilities from their saved planes (the phantom column behaves like one key of its total mass)
                 _ds_from_planes(pp, dP, S * T, npad, float(H) ** -0.5, dsp)
             else:
                 L.check(lib.dost_xattn_softmax_bwd(L.p(scores), L.p(lse), L.p(dP), L.p(g.ptr), L.p(g.nmax), S * T, B, T, npad,
@@ -1591,7 +1598,7 @@ class _SelfAttention(torch.autograd.Function):
                 out = torch.empty(S, Lq, H, dtype=dtype, device=dev)
                 pdp = empty_planes(S * Lq, Lk, dev, _with_lo()) if any(ctx.needs_input_grad[:3]) else None
                 _fused_attention_fwd(qp, kp, S * Lk, S, Lq, Lk, H, None, None, None, Lk, resid.view(S * Lq, H), Lq * H,
-                                     out.view(S * Lq, H), pdp)
+                                     out.view(S * Lq, H), pdp, drop_p, seed)
                 if pdp is not None:
                     ctx.save_for_backward(None, None, *_planes_save(qp), *_planes_save(kp), *_planes_save(pdp))
                 return out
@@ -1669,7 +1676,13 @@ def _self_attention_backward_planes(ctx, d_out):
     gemm_planes(M=Lq, N=Lp, K=H, a=[dop], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=dpd.view(S * Lq, Lp), batch=S,
                 a_bstride=Lq * dop.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
     dsp = empty_planes(S * Lq, Lk, dev, _with_lo())              # dS only ever feeds GEMMs: planes, no fp32 copy
-    if ctx.fused:
+    if ctx.fused and ctx.drop_p > 0:
+        # dropout: the saved planes hold the dropped-out probabilities; P itself is recomputed (scores GEMM + softmax)
+        prob = torch.empty(S, Lq, Lp, dtype=torch.float32, device=dev)
+        gemm_planes(M=Lq, N=Lp, K=H, a=[qp], a_mode=L.KC, b=kp, b_mode=L.KC, b_rows=Lk, out=prob.view(S * Lq, Lp), batch=S,
+                    a_bstride=Lq * qp.ld, b_bstride=Lk * kp.ld, c_bstride=Lq * Lp)
+        L.check(L.lib().dost_softmax_fwd(L.F32, L.p(prob), L.p(prob), None, S * Lq, Lk, Lp, scale, 0.0, 0, L.stream()), "softmax_fwd")
+    if ctx.fused and ctx.drop_p == 0:
         _ds_from_planes(pdp, dpd.view(S * Lq, Lp), S * Lq, Lk, scale, dsp)
     else:
         L.check(L.lib().dost_softmax_bwd_planes(L.p(prob), L.p(dpd), None, S * Lq, Lk, Lp, scale, ctx.drop_p, ctx.seed, L.p(dsp.hi),

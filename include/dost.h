@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 13
+#define DOST_ABI_VERSION 14
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -329,8 +329,11 @@ int dost_softmax_bwd_planes(const float* p, const float* dpd, float* ds, long lo
  *          plane of k_rows rows whose last row per crystal is the phantom key (dost_xattn_kv_ext_build);
  *          that column stands for nmax - (k_count[s] - 1) zero-padded keys (to_dense_batch + LayerNorm,
  *          DOSTransformer.py:61-63).  max_keys >= every k_count[s] (host-side padding length + 1).
- * At most 256 keys per sequence, H in {64, 128, 192, 256}; no dropout (callers use the unfused kernels
- * when attn_drop > 0).  residual: [S, Lq, H] (res_seq_stride = Lq*H) or shared [Lq, H] (0) or NULL.
+ * At most 256 keys per sequence, H in {64, 128, 192, 256}.  drop_p > 0: attention dropout with the
+ * library's counter-based mask (index = row * Lk + key, or row * Nmax + key slot for ragged keys, the
+ * phantom copies surviving individually: the mask of dost_softmax_fwd / dost_xattn_softmax_fwd); the planes
+ * then hold the DROPPED-OUT probabilities and lse (optional, [S*Lq]) the log-sum-exp of the scaled scores,
+ * from which the backward recomputes P.  residual: [S, Lq, H] (res_seq_stride = Lq*H) or shared [Lq, H] (0) or NULL.
  * p_hi / p_lo (optional, [S*Lq, ld_p]): the probabilities as operand planes for the backward pass
  * (phantom column = total probability of its copies; columns past a sequence's keys are zero).
  * dost_softmax_bwd_from_planes: dS = scale * P (dP - sum P dP) per row from those planes -> planes.
@@ -339,7 +342,8 @@ int dost_attn_fused_supported(int Lq, int H, int max_keys);
 int dost_attn_fused_fwd(const void* q_hi, const void* q_lo, long long ld_q, const void* k_hi, const void* k_lo, long long ld_k,
                         long long k_rows, int S, int Lq, int Lk, int H, const int32_t* k_rowoff, const int32_t* k_count,
                         const int32_t* nmax, int max_keys, double scale, const float* residual, long long res_seq_stride,
-                        float* out, void* p_hi, void* p_lo, long long ld_p, int precision, dost_stream_t stream);
+                        float* out, void* p_hi, void* p_lo, long long ld_p, int precision, double drop_p,
+                        unsigned long long seed, float* lse, dost_stream_t stream);
 int dost_softmax_bwd_from_planes(const void* p_hi, const void* p_lo, long long ld_pp, const float* dP, long long ld_dp,
                                  long long rows, int cols, double scale, void* hi, void* lo, long long ldp, dost_stream_t stream);
 

@@ -1135,3 +1135,40 @@ def test_planes_gemm_activation_gate_bits(prec, M, N, K, epi16, monkeypatch):
         # (a positive pre-activation below the smallest bf16 would flush the plane's sign but not the bit: not in this data)
         assert torch.equal(o_bits.hi, o_plane.hi) and (not lo or torch.equal(o_bits.lo, o_plane.lo))
         assert torch.equal(cs_bits, cs_plane)
+
+
+@pytest.mark.parametrize("S,Lq,Lk,H,p", [(4, 201, 201, 256, 0.1), (3, 70, 33, 128, 0.5)])
+def test_fused_attention_dropout_equals_unfused(S, Lq, Lk, H, p):
+    """Attention dropout (multihead_attention.py:71) inside the fused kernel: the same counter-based mask as the softmax kernel
+    of the GEMM + softmax + GEMM formulation (index = row * Lk + key), so the same seed gives the same outputs and gradients
+    (the fused backward recomputes P from the scores, the dropped-out probabilities come from the saved planes); and dropout
+    really happens, deterministically per seed."""
+    q, k = _leaf(_rand(S, Lq, H, dtype=torch.float32, seed=1)), _leaf(_rand(S, Lk, H, dtype=torch.float32, seed=2))
+    r = _leaf(_rand(S, Lq, H, dtype=torch.float32, seed=3))
+    wgt = _rand(S, Lq, H, seed=4)
+    with ops.precision("bf16x3"):
+        res = {}
+        for name in ("fused", "unfused"):
+            for t in (q, k, r):
+                t.grad = None
+            if name == "unfused":
+                import os
+                os.environ["DOST_NO_ATTN_FUSED"] = "1"
+                L.reload_switches()
+            try:
+                n0 = L.launch_count()
+                out = ops.self_attention(q, k, r, p, 777)
+                nl = L.launch_count() - n0
+                (out * wgt).sum().backward()
+            finally:
+                if name == "unfused":
+                    os.environ.pop("DOST_NO_ATTN_FUSED")
+                    L.reload_switches()
+            res[name] = (out.detach(), q.grad.clone(), k.grad.clone(), r.grad.clone(), nl)
+        assert res["fused"][4] == 3 and res["unfused"][4] == 5          # planes of q, k + 1 kernel vs + GEMM, softmax, GEMM
+        for nm, a_, b_ in zip(["out", "dq", "dk", "dr"], res["fused"][:4], res["unfused"][:4]):
+            assert relerr(a_, b_) < 3e-5, (nm, relerr(a_, b_))
+        base = ops.self_attention(q, k, r)
+        again = ops.self_attention(q, k, r, p, 777)
+        other = ops.self_attention(q, k, r, p, 778)
+    assert torch.equal(again, res["fused"][0]) and relerr(other, again) > 1e-3 and relerr(base, again) > 1e-3
