@@ -625,7 +625,7 @@ class _FFNBlock(torch.autograd.Function):
         _, h0p, stats = ln_fwd_planes(y, ln_w, ln_b)
         w1p, w2p = weight_planes(w1), weight_planes(w2)
         h1p = empty_planes(M, F, dev, _with_lo())
-        gate = torch.empty(F // 32, M, dtype=torch.int32, device=dev) if gate_bits_ok(M, F) else None
+        gate = torch.empty(F // 32, M, dtype=torch.int32, device=dev) if (gate_bits_ok(M, F) and any(ctx.needs_input_grad)) else None
         gemm_planes(M=M, N=F, K=H, a=[h0p], a_mode=L.KC, b=w1p, b_mode=L.KC, bias=b1, act=L.ACT_RELU, out_planes=h1p, out_gate=gate)
         out = torch.empty(M, H, dtype=torch.float32, device=dev)
         gemm_planes(M=M, N=H, K=F, a=[h1p], a_mode=L.KC, b=w2p, b_mode=L.KC, bias=b2, residual=y, out=out)
