@@ -34,9 +34,9 @@ __global__ void __launch_bounds__(kSegWarps * 32) segment_reduce_vec_kernel(
 #pragma unroll
     for (int i = 0; i < NV; ++i) acc[i] = Acc<T>::zero();
     // The row indices of (up to) 32 edges are fetched by ONE coalesced load and handed out by shuffles: the row loads of a
-    // group then depend on a single index round trip instead of one per 4 rows, and up to RB rows are in flight per lane.
+    // group then depend on a single index round trip instead of one per 4 rows, and RB rows are in flight per lane (8 measured slower for 256-wide rows: 128 registers, half the resident warps).
     // The sum runs over the edges in ascending CSR order (fixed order, same as before).
-    constexpr int RB = NV <= 2 ? 8 : (NV <= 4 ? 4 : 2);
+    constexpr int RB = NV <= 4 ? 4 : 2;
     for (int base = beg; base < end; base += 32) {
       const int n = min(32, end - base);
       int myrow = base + lane;
