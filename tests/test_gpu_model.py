@@ -440,3 +440,46 @@ def test_fused_adamw_trains_the_tensor_core_path():
             assert float(da.abs().max()) == 0.0, k       # dead parameters stay at their initial values
             continue
         assert float((da - db).norm() / db.norm().clamp_min(1e-30)) < 2e-2, k
+
+
+def test_headline_batch_properties_bf16x3():
+    """BASELINE config 2 at the benchmarked size itself (B = 512 crystals, hidden 256, 3 + 2 layers, T = 201) on the default
+    bf16x3 path, through size-independent properties: finite outputs and gradients; the step is bitwise repeatable; a
+    crystal's prediction depends on its batch companions only through the padding length (64 of the crystals evaluated
+    alone under the same Nmax give the same DOS to the bf16x3 product error); the fused attention kernel and the GEMM +
+    softmax + GEMM formulation give the same loss and gradients (tensor by tensor, 2e-4 rel-L2 of the largest tensors)."""
+    torch.manual_seed(0)
+    m = DOSTransformer(3, 2, 200, 41, 2, 256, torch.device(DEV), 0.0, precision="bf16x3").to(DEV)
+    g = make_edos_batch(512, seed=2000)
+    gd = g.clone().to(DEV)
+    dg, x, ds, loss, grads = _step(m, gd, "edos")
+    assert torch.isfinite(dg).all() and torch.isfinite(ds).all() and torch.isfinite(loss)
+    assert all(torch.isfinite(v).all() for v in grads.values())
+    dg2, _, ds2, loss2, grads2 = _step(m, gd, "edos")
+    assert torch.equal(dg, dg2) and torch.equal(ds, ds2) and torch.equal(loss, loss2)
+    assert all(torch.equal(grads[k], grads2[k]) for k in grads)
+    # the three-kernel attention formulation: same numbers up to the order of the fp32 softmax arithmetic
+    import os
+    from dostransformer_b200 import _lib as L
+    os.environ["DOST_NO_ATTN_FUSED"] = "1"
+    L.reload_switches()
+    try:
+        dg3, _, ds3, loss3, grads3 = _step(m, gd, "edos")
+    finally:
+        os.environ.pop("DOST_NO_ATTN_FUSED")
+        L.reload_switches()
+    assert relerr(dg3, dg) < 1e-4 and relerr(ds3, ds) < 1e-4 and abs(loss3.item() - loss.item()) < 1e-5 * abs(loss.item())
+    for k in grads:
+        a, b = grads[k].double(), grads3[k].double()
+        if b.norm() > 1e-8:
+            assert ((a - b).norm() / b.norm()).item() < 2e-3, k
+    # companions only matter through Nmax
+    n = torch.bincount(g.batch)
+    ids = list(range(0, 512, 8))
+    m.eval()
+    with torch.no_grad():
+        full = m(gd)[0]
+        m.max_num_nodes = int(n.max())
+        part = m(_subset(g, ids).to(DEV))[0]
+        m.max_num_nodes = None
+    assert relerr(part, full[ids]) < 1e-4
