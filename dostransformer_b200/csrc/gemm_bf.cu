@@ -35,6 +35,7 @@ struct Maps {
   CUtensorMap b_hi2, b_lo2;      // K-major B with a 128-row box (CTA pair: each CTA stages half of the 256 output columns)
   // TMA-store epilogue (Params::tma_epi): fp32 out {32 columns, 32 rows} boxes, SWIZZLE_128B; bf16 planes {32, 32}, SWIZZLE_64B
   CUtensorMap c_out, c_hi, c_lo;
+  CUtensorMap c_pre;             // the pre-activation copy (out_pre), same box as c_out
 };
 
 struct Params {
@@ -564,6 +565,26 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
         const bool row_ok = mrow < Mv;
         const bool warp_rows_ok = t.m0 + quad * 32 < Mv;
         uint32_t gate_acc = 0u;
+        // fp32 values of this chunk -> staging tile (rows of CW * 4 bytes in the TMA swizzle of that pitch: 128 B: row & 7,
+        // 64 B: (row >> 1) & 3) -> one bulk-tensor store: kind 0 = out, 1 = out_pre, 2 = out += (reduction store)
+        auto stage_f32 = [&](const float (&val)[CW], int kind, int n0s) {
+          if (lane == 0) bulk_wait_read0();                  // the previous store has finished READING the tile
+          __syncwarp();
+          const uint32_t swf = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j)
+            sts128(stg + lane * (CW * 4) + ((j ^ swf) << 4), __float_as_uint(val[4 * j]), __float_as_uint(val[4 * j + 1]),
+                   __float_as_uint(val[4 * j + 2]), __float_as_uint(val[4 * j + 3]));
+          fence_async_smem();                                // generic-proxy smem writes -> visible to the async proxy (TMA)
+          __syncwarp();
+          if (lane == 0) {
+            const int mw = t.m0 + quad * 32;
+            const int zc = (p.zmode == 1) ? t.z : 0;        // batched: the box never spans two problems (rows >= M clipped)
+            if (kind == 2) tma_reduce_add_3d(&maps.c_out, stg, n0s, mw, zc);
+            else tma_store_3d(kind == 1 ? &maps.c_pre : &maps.c_out, stg, n0s, mw, zc);
+            bulk_commit();
+          }
+        };
 #pragma unroll 1
         for (int c0 = 0; c0 < CH; c0 += CW) {
           const int n0 = t.n0 + half * CH + c0;            // first column of the chunk (warp-uniform)
@@ -599,6 +620,7 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
               v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
             }
           }
+          if (feat & F_PRE) stage_f32(v, 1, n0);
           if (feat & F_GATE_OUT) {
             uint32_t bits = 0u;
 #pragma unroll
@@ -647,51 +669,37 @@ __global__ void __launch_bounds__((EW + 2) * 32, 1) gemm_bf_kernel(const __grid_
           // `pre` is consumed: the next chunk's side inputs fly during the staging / store of this chunk and the first
           // half of the next one
           if ((feat & (F_RES | F_DACT)) && c0 + CW < CH) prefetch_side(c0 + CW);
-          {
-            // the previous chunk's store must have finished READING the staging tile before it is overwritten
+          // One staging tile per warp, used once per kind of output of this chunk (pre-activation copy above, fp32 result,
+          // bf16 planes): every use first waits until the previous store has READ the tile.
+          if (feat & F_OUT) stage_f32(v, (feat & F_ACC) ? 2 : 0, n0);
+          if (feat & F_HI) {
             if (lane == 0) bulk_wait_read0();
             __syncwarp();
-            // staging rows are CW * 4 (fp32) or CW * 2 (bf16) bytes; 16-byte column chunk c of row `lane` goes to chunk
-            // c ^ swz, swz = the TMA swizzle of that row pitch (128 B: row & 7; 64 B: (row >> 1) & 3; 32 B: (row >> 2) & 1)
-            if (feat & F_OUT) {
-              const uint32_t swf = CW == 32 ? (lane & 7) : ((lane >> 1) & 3);
+            uint32_t hi[CW / 2];
 #pragma unroll
-              for (int j = 0; j < CW / 4; ++j)
-                sts128(stg + lane * (CW * 4) + ((j ^ swf) << 4), __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
-                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
-            } else {                                         // bf16 hi (and lo) planes
-              uint32_t hi[CW / 2];
+            for (int j = 0; j < CW / 2; ++j) hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+            const uint32_t sw = CW == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
 #pragma unroll
-              for (int j = 0; j < CW / 2; ++j) hi[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-              const uint32_t sw = CW == 32 ? ((lane >> 1) & 3) : ((lane >> 2) & 1);
+            for (int c = 0; c < CW / 8; ++c)
+              sts128(stg + lane * (CW * 2) + ((c ^ sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            if (feat & F_LO) {
 #pragma unroll
-              for (int c = 0; c < CW / 8; ++c)
-                sts128(stg + lane * (CW * 2) + ((c ^ sw) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-              if (feat & F_LO) {
+              for (int c = 0; c < CW / 8; ++c) {
+                uint32_t lo[4];
 #pragma unroll
-                for (int c = 0; c < CW / 8; ++c) {
-                  uint32_t lo[4];
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const int j = 4 * c + q;
-                    lo[q] = pack_bf16(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xFFFF0000u));
-                  }
-                  sts128(stg + 64 * CW + lane * (CW * 2) + ((c ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+                for (int q = 0; q < 4; ++q) {
+                  const int j = 4 * c + q;
+                  lo[q] = pack_bf16(v[2 * j] - __uint_as_float(hi[j] << 16), v[2 * j + 1] - __uint_as_float(hi[j] & 0xFFFF0000u));
                 }
+                sts128(stg + 64 * CW + lane * (CW * 2) + ((c ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
               }
             }
             fence_async_smem();                              // generic-proxy smem writes -> visible to the async proxy (TMA)
             __syncwarp();
             if (lane == 0) {
               const int mw = t.m0 + quad * 32;
-              const int zc = (p.zmode == 1) ? t.z : 0;      // batched: the box never spans two problems (rows >= M clipped)
-              if (feat & F_OUT) {
-                if (feat & F_ACC) tma_reduce_add_3d(&maps.c_out, stg, n0, mw, zc);
-                else tma_store_3d(&maps.c_out, stg, n0, mw, zc);
-              } else {
-                tma_store_3d(&maps.c_hi, stg, n0, mw, zc);
-                if (feat & F_LO) tma_store_3d(&maps.c_lo, stg + 64 * CW, n0, mw, zc);
-              }
+              tma_store_3d(&maps.c_hi, stg, n0, mw, 0);
+              if (feat & F_LO) tma_store_3d(&maps.c_lo, stg + 64 * CW, n0, mw, 0);
               bulk_commit();
             }
           }
@@ -1393,28 +1401,32 @@ static int run(const dost_gemm_bf16_t* h, void* workspace, size_t workspace_byte
   DOST_REQUIRE(!h->out_hi || (((uintptr_t)h->out_hi & 7) == 0 && ((uintptr_t)h->out_lo & 7) == 0 && h->ld_op % 4 == 0),
                "gemm_bf16: output plane alignment");
 
-  // ---- TMA-store epilogue: exactly one kind of output, no pre-activation copy / split-K / ragged rows (an accumulating fp32
-  // output becomes a TMA reduction store)
+  // ---- TMA-store epilogue: no split-K / ragged rows; the fp32 result, its pre-activation copy and the bf16 planes go out
+  // one after the other through the warp's staging tile (an accumulating fp32 output becomes a TMA reduction store)
   p.tma_epi = 0;
   bool ew16 = false;
   maps.c_out = maps.b_hi;
   maps.c_hi = maps.b_hi;
   maps.c_lo = maps.b_hi;
-  if (tma_epi_enabled() && split == 1 && !h->out_pre && !(h->accumulate && h->out_hi) && !p.c_rowoff && !p.c_rowlim &&
-      ((h->out != nullptr) != (h->out_hi != nullptr)) && h->M >= 32 && h->N >= 32 && !(h->dact_hi && h->residual) &&
+  maps.c_pre = maps.b_hi;
+  if (tma_epi_enabled() && split == 1 && !(h->accumulate && h->out_hi) && !p.c_rowoff && !p.c_rowlim &&
+      !(h->out_pre && !h->out) && (batch == 1 || !h->out_hi) && h->M >= 32 && h->N >= 32 && !(h->dact_hi && h->residual) &&
       (!h->dact_hi || (al16(h->dact_hi) && h->ld_dact % 8 == 0))) {
     int rc2 = DOST_OK;
     // CTA-pair launches run 16 epilogue warps on 16-column chunks (DOST_GEMM_EPI16=0: 8 warps on 32-column chunks; =2:
     // also with fused column sums, where 16 warps measured 16 % slower: 0.400 -> 0.464 ms at the FFN's fc2 input gradient)
     ew16 = pairs && epi16_enabled(h->colsum != nullptr);
     const int bc = ew16 ? 16 : 32;
-    if (h->out) {     // (batched problems: fp32 stores only, checked above)
-      rc2 = make_out_map(&maps.c_out, h->out, true, bc, h->N, h->M, h->ldc, batch, h->c_bstride);
-    } else if (al16(h->out_hi) && al16(h->out_lo) && h->ld_op % 8 == 0) {
-      rc2 = make_out_map(&maps.c_hi, h->out_hi, false, bc, h->N, h->M, h->ld_op);
-      if (rc2 == DOST_OK && h->out_lo) rc2 = make_out_map(&maps.c_lo, h->out_lo, false, bc, h->N, h->M, h->ld_op);
-    } else {
-      rc2 = DOST_ERR_ARG;
+    // every kind of output the launch has: fp32 result, pre-activation copy (same shape), bf16 planes (single problems only)
+    if (h->out) rc2 = make_out_map(&maps.c_out, h->out, true, bc, h->N, h->M, h->ldc, batch, h->c_bstride);
+    if (rc2 == DOST_OK && h->out_pre) rc2 = make_out_map(&maps.c_pre, h->out_pre, true, bc, h->N, h->M, h->ld_pre);
+    if (rc2 == DOST_OK && h->out_hi) {
+      if (al16(h->out_hi) && al16(h->out_lo) && h->ld_op % 8 == 0) {
+        rc2 = make_out_map(&maps.c_hi, h->out_hi, false, bc, h->N, h->M, h->ld_op);
+        if (rc2 == DOST_OK && h->out_lo) rc2 = make_out_map(&maps.c_lo, h->out_lo, false, bc, h->N, h->M, h->ld_op);
+      } else {
+        rc2 = DOST_ERR_ARG;
+      }
     }
     if (rc2 == DOST_OK) p.tma_epi = 1;       // (a shape the encoder rejects simply keeps the register epilogue)
     else ew16 = false;

@@ -962,11 +962,19 @@ def test_planes_gemm_tma_store_epilogue_equals_register_epilogue(prec, M, N, K, 
             ops.gemm_planes(M=Mb, N=Nb, K=K, a=[qa], a_mode=L.KC, b=kb, b_mode=L.KC, b_rows=Nb, out=ob2, accumulate=True, batch=nb_,
                             a_bstride=Mb * qa.ld, b_bstride=Nb * kb.ld, c_bstride=Mb * Nb)
             outs["acc_batched"] = ob2
+            # (7) every kind of output in one launch (the edge block's second Linear: v, e + v and the planes of e + v)
+            o7, pre7 = torch.full((M, N), float("nan"), device=DEV), torch.full((M, N), float("nan"), device=DEV)
+            p7 = ops.empty_planes(M, N, DEV, with_lo=lo)
+            p7.hi.fill_(float("nan"))
+            ops.gemm_planes(M=M, N=N, K=K, a=[ap], a_mode=L.KC, b=wp, b_mode=bm, bias=bias, out_pre=pre7, residual=res, out=o7,
+                            out_planes=p7)
+            outs["multi_out"], outs["multi_pre"] = o7, pre7
+            outs["multi_hi"], outs["multi_lo"] = p7.hi[:, :N], (p7.lo[:, :N] if lo else None)
         torch.cuda.synchronize()
         return outs
 
     reg, tma = run(False), run(True)
-    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide", "batched", "acc", "acc_batched"):
+    for k in ("fp32", "hi", "lo", "hi3", "lo3", "wide", "batched", "acc", "acc_batched", "multi_out", "multi_pre", "multi_hi", "multi_lo"):
         if reg[k] is None:
             continue
         assert not torch.isnan(tma[k].float()).any(), k
