@@ -469,6 +469,8 @@ def timed_steps(step, batches, steps, warmup, barrier, st, ncu_window=False):
         if ncu_window and i == 0:       # `ncu --profile-from-start off python bench.py --ncu-window`: the launch list of
             torch.cuda.cudart().cudaProfilerStart()      # exactly one timed step of this very command
         step(batches[i % len(batches)])
+        if os.environ.get("DOST_BENCH_SYNC_EACH"):       # (debugging aid)
+            torch.cuda.synchronize()
         if ncu_window and i == 0:
             torch.cuda.synchronize()
             torch.cuda.cudart().cudaProfilerStop()
@@ -751,7 +753,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
     strong = args.scaling == "strong"
     use_graph = {"on": True, "off": False, "auto": True}[args.graph]
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("DOST_BENCH_NO_SAMPLER"):
         sampler.start()
 
     if strong:
@@ -864,7 +866,7 @@ def run_product(args, rank: int, world: int, local_rank: int):
         guarded("strong_scaling", lambda: strong_scaling_leg(model, rank, world, dev, args.steps, args.warmup, barrier, st, 512,
                                                              True, L))
         guarded("large_cell", lambda: weak_leg(
-            model, "large", "edos", 64, rank, world, dev, max(4, args.steps // 2), 3, barrier, st, False, L,
+            model, "large", "edos", 64, rank, world, dev, max(4, args.steps // 2), 3, barrier, st, use_graph, L,
             f"{MODEL_DESC} T={T}, large-cell stress shape (BASELINE configs[3]: 200-400 atoms, 24 neighbours), 64 crystals per GPU"))
         guarded("sweep", lambda: sweep_leg(model, rank, world, dev, args.sweep_per_gpu, args.sweep_store, args.sweep_batch, barrier))
     if world == 1 and extras:

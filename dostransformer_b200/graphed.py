@@ -160,7 +160,9 @@ class GraphedStep:
         # thread_local: other threads of the process (NCCL's watchdog polling its events, the autograd engine's worker
         # that launches the backward kernels into this capture) stay unrestricted; only this thread may not issue
         # capture-unsafe calls
-        with torch.cuda.graph(e.graph, pool=self._pool, stream=s, capture_error_mode="thread_local"):
+        import os
+        pool = None if os.environ.get("DOST_GRAPH_PRIVATE_POOLS") else self._pool
+        with torch.cuda.graph(e.graph, pool=pool, stream=s, capture_error_mode="thread_local"):
             e.out = self._eager(e.static, refresh=True, leaves=e.leaves)
         e.launches = L.launch_count() - l0
         # the gradient buffers this graph writes (graph-pool memory, fixed addresses): re-attached on every replay, since

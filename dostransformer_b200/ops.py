@@ -1098,11 +1098,19 @@ def _const(value: float, dtype, device) -> torch.Tensor:
     return _CONST_CACHE[key]
 
 
+_ARANGE_RETIRED = []     # outgrown index tensors stay alive: captured CUDA graphs (graphed.GraphedStep) hold their addresses
+
+
 def _arange_i32(n: int, device) -> torch.Tensor:
     key = (str(device), )
     cur = _ARANGE_CACHE.get(key)
     if cur is None or cur.numel() < n:
-        cur = torch.arange(max(n, 1 << 16), dtype=torch.int32, device=device)
+        if cur is not None:
+            # never free the old one: a graph captured while it was current replays kernels that read it (a freed block is
+            # re-used by the allocator and the graph then gathers through garbage indices: an illegal address in the
+            # large-cell bench, where the second batch has more edges than the first)
+            _ARANGE_RETIRED.append(cur)
+        cur = torch.arange(max(2 * n, 1 << 20), dtype=torch.int32, device=device)
         _ARANGE_CACHE[key] = cur
     return cur[:n]
 

@@ -121,3 +121,37 @@ def test_graphed_inference_matches_eager():
         for a, b in zip(got, want):
             assert torch.equal(a, b)
     assert step.captures == 1
+
+
+def test_cached_index_tensors_outlive_captured_graphs():
+    """ops._arange_i32 hands out views of one cached index tensor and replaces it when a larger one is needed.  A CUDA graph
+    captured before the replacement still reads the OLD tensor on every replay: it must stay alive (it used to be freed,
+    its block re-used, and the large-cell bench - second batch with more edges than the first - gathered through garbage
+    indices: an illegal address)."""
+    import torch
+    from dostransformer_b200 import ops
+    dev = torch.device("cuda")
+    n1 = 5000
+    a = torch.randn(n1, 64, device=dev)
+    b = torch.randn(n1, 64, device=dev)
+    out = torch.empty(n1, 64, device=dev)
+    ops._axpy2(a, b, out)                         # warm-up outside the capture (creates / uses the cached index tensor)
+    torch.cuda.synchronize()
+    key = (str(a.device),)
+    old = ops._ARANGE_CACHE[key]
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            ops._axpy2(a, b, out)                 # gather_rows with the identity index: reads the cached tensor
+    torch.cuda.current_stream().wait_stream(s)
+    big = ops._arange_i32(old.numel() + 1, a.device)   # outgrows the cache: a new tensor replaces the old one
+    assert ops._ARANGE_CACHE[key].data_ptr() != old.data_ptr()
+    del old, big
+    junk = [torch.full((1 << 20,), -7, dtype=torch.int32, device=dev) for _ in range(8)]     # would re-use a freed block
+    out.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, a + b)
+    del junk
