@@ -180,7 +180,8 @@ class GraphedStep:
             if self.train and self.world > 1:
                 allreduce_gradients(self._params, self.group)
             return out
-        sig = batch_signature(g)
+        # (the model's data-parallel padding length is a host integer baked into the captured launches: part of the key)
+        sig = batch_signature(g) + (("model_max_num_nodes", getattr(self.model, "max_num_nodes", None)),)
         e = self._entries.get(sig)
         if e is None:
             if len(self._entries) >= self.max_graphs:

@@ -155,3 +155,21 @@ def test_cached_index_tensors_outlive_captured_graphs():
     torch.cuda.synchronize()
     assert torch.equal(out, a + b)
     del junk
+
+
+def test_graph_replay_follows_the_models_padding_length():
+    """model.max_num_nodes (the data-parallel global padding length set by the sharder) is a host integer baked into the
+    captured launches: the graph cache is keyed on it, so a change between two steps with identical batch shapes gives the
+    eager result for the NEW value (more phantom keys) instead of a stale replay."""
+    m = _model()
+    step = GraphedStep(m, "edos")
+    g = make_edos_batch(5, seed=41, mean_atoms=8.0).to(DEV)
+    losses = {}
+    for nm in (None, g.max_num_nodes + 9, None, g.max_num_nodes + 9):
+        m.max_num_nodes = nm
+        want, _ = _eager(m, g)
+        got = step(g)
+        assert torch.equal(got.detach(), want), nm
+        losses[nm] = want.item()
+    m.max_num_nodes = None
+    assert step.captures == 2 and losses[None] != losses[g.max_num_nodes + 9]
