@@ -22,7 +22,7 @@ PREC_FMA, PREC_BF16X3, PREC_BF16 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FMA, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
 
 _lib: Optional[C.CDLL] = None
-ABI_VERSION = 14
+ABI_VERSION = 15
 DEVERR_MESSAGES = {1: "an index (edge_index / batch / system) is outside its table",
                    2: "a crystal has more atoms than the padding length given by the host (max_num_nodes)"}
 
@@ -127,6 +127,8 @@ _SIGNATURES = {
     "dost_gather_rows": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p]),
     "dost_phonon_edge_feat": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "dost_phonon_edge_encode": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
     "dost_xattn_fwd": (C.c_int, [C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_double, C.c_double, C.c_ulonglong, C.c_void_p]),

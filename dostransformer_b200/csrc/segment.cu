@@ -242,6 +242,39 @@ __global__ void phonon_edge_feat_kernel(const T* __restrict__ vec, long long E, 
   out[4 * e + 3] = cut * s3 * z * inv;
 }
 
+// The same features computed INSIDE the first Linear of the edge encoder (DOSTransformer_phonon.py:74-77 -> GN_encoder.
+// edge_encoder[0..1]): pre[e, c] = b[c] + sum_k W[c, k] feat_k(edge_vec[e]); out = PReLU(pre).  The [E, 4] feature tensor
+// never exists.  One warp per edge: the 4 features are computed once per lane, lanes cover the H columns (coalesced rows).
+template <typename T>
+__global__ void __launch_bounds__(256) phonon_edge_encode_kernel(const T* __restrict__ vec, long long E, const T* __restrict__ W,
+                                                                 const T* __restrict__ bias, const T* __restrict__ slope_p, int H,
+                                                                 T* __restrict__ pre, T* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long e = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (e >= E) return;
+  const T x = vec[3 * e], y = vec[3 * e + 1], z = vec[3 * e + 2];
+  const T len = sqrt(x * x + y * y + z * z);
+  const T inv = T(1) / max(len, T(1e-12));
+  const T u = T(2) * (len / T(4) - T(1));
+  T cut;
+  if (u > T(0)) cut = T(0);
+  else if (u < T(-1)) cut = T(1);
+  else cut = (T(1) - cos(T(3.14159265358979323846) * u)) / T(2);
+  const T s3 = T(1.7320508075688772935);
+  const T f0 = cut, f1 = cut * s3 * x * inv, f2 = cut * s3 * y * inv, f3 = cut * s3 * z * inv;
+  const T slope = slope_p ? slope_p[0] : T(1);
+  for (int c = lane; c < H; c += 32) {
+    // the accumulation order of the generic GEMM kernel (k ascending, fused multiply-adds, bias last)
+    T v = fma(W[4 * c + 0], f0, T(0));
+    v = fma(W[4 * c + 1], f1, v);
+    v = fma(W[4 * c + 2], f2, v);
+    v = fma(W[4 * c + 3], f3, v);
+    if (bias) v += bias[c];
+    if (pre) pre[e * H + c] = v;
+    out[e * H + c] = (v > T(0)) ? v : slope * v;
+  }
+}
+
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename T>
@@ -343,4 +376,23 @@ extern "C" int dost_phonon_edge_feat(int dtype, const void* edge_vec, long long 
     return DOST_ERR_UNSUPPORTED;
   }
   return check_launch("phonon_edge_feat");
+}
+
+extern "C" int dost_phonon_edge_encode(int dtype, const void* edge_vec, long long E, const void* weight, const void* bias,
+                                       const void* prelu_slope, int H, void* pre, void* out, dost_stream_t stream) {
+  if (E == 0) return DOST_OK;
+  DOST_REQUIRE(edge_vec && weight && out && E > 0 && H > 0, "phonon_edge_encode: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((E + 7) / 8);
+  if (dtype == DOST_F32)
+    phonon_edge_encode_kernel<float><<<blocks, 256, 0, st>>>((const float*)edge_vec, E, (const float*)weight, (const float*)bias,
+                                                             (const float*)prelu_slope, H, (float*)pre, (float*)out);
+  else if (dtype == DOST_F64)
+    phonon_edge_encode_kernel<double><<<blocks, 256, 0, st>>>((const double*)edge_vec, E, (const double*)weight, (const double*)bias,
+                                                              (const double*)prelu_slope, H, (double*)pre, (double*)out);
+  else {
+    set_error("phonon_edge_encode: unsupported dtype %d", dtype);
+    return DOST_ERR_UNSUPPORTED;
+  }
+  return check_launch("phonon_edge_encode");
 }

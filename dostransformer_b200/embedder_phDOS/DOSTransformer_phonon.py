@@ -70,10 +70,12 @@ class DOSTransformer_phonon(nn.Module):
                                 phantoms=not (self.per_crystal_eval and not self.training))
         seeds = K._Seeds(self.attn_drop, self.training)
         dtype = self.fc.weight.dtype
-        edge_attr = ops.phonon_edge_features(g["edge_vec"].to(dtype))
         enc = self.GN_encoder
         x = K.mlp_prelu(enc.node_encoder, g.x.to(dtype))
-        e = K.mlp_prelu(enc.edge_encoder, edge_attr)
+        # edge features (sh(l <= 1) x smooth cutoff of edge_vec, :74-77) are computed inside the edge encoder's first Linear
+        ee = enc.edge_encoder
+        e = ops.phonon_edge_encode(g["edge_vec"].to(dtype), ee[0].weight, ee[0].bias, ee[1].weight)
+        e = ops.linear([(e, None)], ee[2].weight, ee[2].bias)
         x = K.message_passing(self.stacked_processor, x, e, graph, mean=True)
         pooled = ops.segment_reduce(x, graph.crystals, False)
         dec = self.GN_decoder.mlp[0]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DOST_ABI_VERSION 14
+#define DOST_ABI_VERSION 15
 
 enum { DOST_F32 = 0, DOST_F64 = 1 };
 enum { DOST_OK = 0, DOST_ERR_ARG = -1, DOST_ERR_LAUNCH = -2, DOST_ERR_WORKSPACE = -3, DOST_ERR_UNSUPPORTED = -4 };
@@ -259,6 +259,11 @@ int dost_gather_rows(int dtype, const void* src, long long ld, const int32_t* id
 
 /* Phonon edge features: smooth_cutoff(|v|/4) * [1, sqrt(3) v/|v|] (DOSTransformer_phonon.py:75-77). */
 int dost_phonon_edge_feat(int dtype, const void* edge_vec, long long E, void* out, dost_stream_t stream);
+/* the same features computed inside the first Linear of the edge encoder (GN_encoder.edge_encoder[0..1],
+ * DOSTransformer_phonon.py:74-77): pre[e, :] = weight [H, 4] . feat(edge_vec[e]) + bias, out = PReLU(pre); the [E, 4] feature
+ * tensor is never written.  pre may be NULL (inference). */
+int dost_phonon_edge_encode(int dtype, const void* edge_vec, long long E, const void* weight, const void* bias,
+                            const void* prelu_slope, int H, void* pre, void* out, dost_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Ragged energy->atom cross attention with analytic phantom keys: to_dense_batch zero padding +

@@ -1180,3 +1180,37 @@ def test_fused_attention_dropout_equals_unfused(S, Lq, Lk, H, p):
         again = ops.self_attention(q, k, r, p, 777)
         other = ops.self_attention(q, k, r, p, 778)
     assert torch.equal(again, res["fused"][0]) and relerr(other, again) > 1e-3 and relerr(base, again) > 1e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_phonon_edge_encode_fused(dtype):
+    """Edge features computed inside the edge encoder's first Linear (DOSTransformer_phonon.py:74-77 ->
+    GN_encoder.edge_encoder): same fma chain as features -> GEMM -> PReLU, so the forward is bitwise that composition; the
+    weight / bias / slope gradients agree with it and with the torch restatement (zero-length edge vectors included)."""
+    E, H = 3001, 256
+    ev = _rand(E, 3, dtype=dtype, seed=1, scale=2.0)
+    ev[::97] = 0
+    w, b = _leaf(_rand(H, 4, dtype=dtype, seed=2)), _leaf(_rand(H, dtype=dtype, seed=3))
+    slope = _leaf(torch.tensor([0.25], dtype=dtype, device=DEV))
+    wgt = _rand(E, H, dtype=dtype, seed=4)
+
+    def fused():
+        return ops.phonon_edge_encode(ev, w, b, slope)
+
+    def composed():
+        return ops.linear([(ops.phonon_edge_features(ev), None)], w, b, act=L.ACT_PRELU, prelu_slope=slope)
+
+    def ref():
+        f = O.phonon_edge_features(ev.double()) if hasattr(O, "phonon_edge_features") else ops.phonon_edge_features(ev).double()
+        return torch.nn.functional.prelu(f @ w.double().T + b.double(), slope.double())
+
+    with ops.precision("fp32"):
+        o1, g1 = _grads(lambda: fused() * wgt, [w, b, slope])
+        o2, g2 = _grads(lambda: composed() * wgt, [w, b, slope])
+    assert torch.equal(o1[0], o2[0])
+    for a_, b_ in zip(g1, g2):
+        assert relerr(a_, b_) < TOL[dtype] * 10
+    o3, g3 = _grads(lambda: ref() * wgt.double(), [w, b, slope])
+    assert relerr(o1[0], o3[0]) < TOL[dtype] * 5
+    for a_, b_ in zip(g1, g3):
+        assert relerr(a_, b_) < TOL[dtype] * 20

@@ -113,7 +113,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/dost.h but not exported"
     assert declared == set(_lib.EXPORTED_SYMBOLS)
-    assert lib.dost_abi_version() == _lib.ABI_VERSION == 14
+    assert lib.dost_abi_version() == _lib.ABI_VERSION == 15
     # argument validation works without a GPU (no launch happens)
     assert lib.dost_gemm(None, None, 0, None) == -1
     assert b"null descriptor" in lib.dost_last_error()
