@@ -294,3 +294,32 @@ def test_staged_reference_copy_is_byte_identical():
     for rel, sha in man["sha256"].items():
         with open(os.path.join("/root/reference", rel), "rb") as f:
             assert hashlib.sha256(f.read()).hexdigest() == sha, rel
+
+
+def test_kernel_path_gates_are_host_decisions(monkeypatch):
+    """Which kernels a call takes is decided on the host from shapes, the precision context and the DOST_* switches: the
+    fused attention (<= 256 keys, H in {64, 128, 192, 256}, a tensor-core precision), the 1-bit ReLU gates of the FFN (TMA-store
+    epilogue: M >= 32, N % 32 == 0), the key-side buffer bound of the attention (the batch's own largest crystal, not the
+    data-parallel padding length).  No device is touched."""
+    from dostransformer_b200 import _lib as L
+    from dostransformer_b200 import ops
+    with ops.precision("bf16x3"):
+        assert ops.fused_attention_ok(256, 201) and ops.fused_attention_ok(128, 1, 0.3) and ops.fused_attention_ok(64, 256)
+        assert not ops.fused_attention_ok(256, 257) and not ops.fused_attention_ok(32, 40) and not ops.fused_attention_ok(320, 40)
+        monkeypatch.setenv("DOST_NO_ATTN_FUSED", "1")
+        L.reload_switches()
+        assert not ops.fused_attention_ok(256, 201)
+        monkeypatch.delenv("DOST_NO_ATTN_FUSED")
+        L.reload_switches()
+    with ops.precision("fp32"):
+        assert not ops.fused_attention_ok(256, 201)
+    assert ops.gate_bits_ok(205824, 1024) and not ops.gate_bits_ok(16, 1024) and not ops.gate_bits_ok(4096, 1000)
+    monkeypatch.setenv("DOST_GEMM_TMA_EPI", "0")
+    assert not ops.gate_bits_ok(205824, 1024)
+    monkeypatch.delenv("DOST_GEMM_TMA_EPI")
+    t = torch.zeros(1, dtype=torch.int32)
+    csr = ops.CSR(t, None, t, 0)
+    g = ops.CrystalGraph(0, 0, 0, t, t, t, t, csr, csr, csr, csr, t, 201, 111)
+    assert g.nkeys_host == 112                       # own largest crystal (111) + the phantom column, not the global 201
+    assert ops.CrystalGraph(0, 0, 0, t, t, t, t, csr, csr, csr, csr, t, 201, None).nkeys_host == 202
+    assert ops.CrystalGraph(0, 0, 0, t, t, t, t, csr, csr, csr, csr, t, None, None).nkeys_host is None
