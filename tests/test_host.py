@@ -323,3 +323,40 @@ def test_kernel_path_gates_are_host_decisions(monkeypatch):
     assert g.nkeys_host == 112                       # own largest crystal (111) + the phantom column, not the global 201
     assert ops.CrystalGraph(0, 0, 0, t, t, t, t, csr, csr, csr, csr, t, 201, None).nkeys_host == 202
     assert ops.CrystalGraph(0, 0, 0, t, t, t, t, csr, csr, csr, csr, t, None, None).nkeys_host is None
+
+
+def test_index_cache_keeps_outgrown_tensors_alive():
+    """ops._arange_i32 serves views of one cached index tensor per device.  When a longer one is needed the old tensor is
+    retired, not freed: launches recorded in a CUDA graph keep reading it (the GPU-side regression is
+    tests/test_gpu_graphed.py::test_cached_index_tensors_outlive_captured_graphs)."""
+    from dostransformer_b200 import ops
+    dev = torch.device("cpu")
+    a = ops._arange_i32(10, dev)
+    base = ops._ARANGE_CACHE[(str(dev),)]
+    assert a.data_ptr() == base.data_ptr() and torch.equal(a, torch.arange(10, dtype=torch.int32))
+    n_retired = len(ops._ARANGE_RETIRED)
+    b = ops._arange_i32(base.numel() + 5, dev)
+    assert b.numel() == base.numel() + 5 and int(b[-1]) == base.numel() + 4
+    assert ops._ARANGE_CACHE[(str(dev),)] is not base
+    assert len(ops._ARANGE_RETIRED) == n_retired + 1 and ops._ARANGE_RETIRED[-1] is base
+    assert torch.equal(a, torch.arange(10, dtype=torch.int32))          # the earlier view still reads its own storage
+    c = ops._arange_i32(7, dev)                                          # smaller requests re-use the new tensor
+    assert c.data_ptr() == ops._ARANGE_CACHE[(str(dev),)].data_ptr() and len(ops._ARANGE_RETIRED) == n_retired + 1
+
+
+def test_reference_arm_under_torchrun_prints_one_line():
+    """The driver launches both arms the same way.  Under torch.distributed.run with 2 ranks the reference arm runs on
+    rank 0 alone and prints ONE JSON line; rank 1 exits 0 without work."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--gpus", "2", "--steps", "1", "--warmup", "0", "--cpu-sample", "4"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0 and d["e2e"]["value"] == d["value"]
