@@ -307,7 +307,8 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
     nbytes = 4.0 * HIDDEN * (gr.E + gr.N) + 4.0 * gr.E + 4.0 * (gr.N + 1)
     gbs = nbytes / sec / 1e9
     out["roofline_hbm"] = {"kernel": "segment_reduce_vec_kernel<float,2> (scatter_sum [E,256]->[N,256])", "bound": "hbm",
-                           "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None,
+                           "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+                           "traffic": ncu_capture("r2_ncu_streaming_segment_reduce") if B == 512 else None,
                            "algorithmic_bytes_per_launch": nbytes, "launch_ms": sec * 1e3, "E": gr.E, "N": gr.N,
                            "note": "inputs rotated over >300 MB so they do not sit in L2"}
     del big
@@ -353,7 +354,11 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
             out["roofline_attention"] = {
                 "kernel": "fa::attn_fwd_kernel (QK^T -> fp32 softmax in TMEM -> PK, one kernel), energy self attention [2B, 201, 256]",
                 "bound": "tensor", "achieved": fl / sec / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": fl / sec / 1e12 / pk["tensor"],
-                "traffic": None, "algorithmic_flops_per_launch": fl, "launch_ms": sec * 1e3,
+                "traffic": ncu_capture("r2_ncu_attn_self") if (B == 512 and precision == "bf16x3") else None,
+                "traffic_note": "ncu --set full capture (profiles/r2_ncu_attn_self.summary.txt) of this kernel inside a training step, "
+                                "where it also writes the bf16 probability planes the backward reads (about 170 MB more than the "
+                                "forward-only launch timed here)",
+                "algorithmic_flops_per_launch": fl, "launch_ms": sec * 1e3,
                 "tensor_pipe_frac": fl * mult / sec / 1e12 / pk["tensor"],
                 "hbm_gbytes_per_s": 3.0 * S2 * T * HIDDEN * 4 / sec / 1e9,
                 "note": "201 queries / keys occupy 256-wide tiles (62 % of the issued MMA work is algorithmic); q, residual and out "
@@ -381,6 +386,16 @@ def kernel_rooflines(B: int, pk, precision: str, traffic):
                 "note": "ragged keys (mean 25 per crystal) against 128-query tiles: bound by the q / residual / out streams, "
                         + f"{3.0 * S2 * T * HIDDEN * 4 / sec / 1e9:.0f} GB/s of {pk['hbm']:.0f}; includes the key-plane build kernel"}
     return out
+
+
+def ncu_capture(name: str):
+    """dram bytes (read + write) per launch of one named `ncu --set full` capture recorded in profiles/ncu_gemm_traffic.json
+    (the summaries themselves are profiles/<name>.summary.txt); None when the capture is not there."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_gemm_traffic.json")) as f:
+            return json.load(f).get("captures", {}).get(name)
+    except Exception:
+        return None
 
 
 def ncu_traffic(precision: str):
